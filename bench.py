@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — QA-rounds/s of one training step of the hot path (BASELINE.json metric).
+
+A "step" = Model:trainIteration minus data loading (model.lua:66-106): zeroGradParameters, forward,
+criterion, backward, [gradient all-reduce], clamp(-5,5), adam — on one synthetic VisDial-shaped batch of
+B dialogs (x10 rounds x100 options) per GPU for `mn-att-ques-im-hist + disc` (BASELINE config 4).
+
+  value : whole-job QA-rounds/s with the batch already resident in HBM (device-timed, max over ranks)
+  e2e   : the same step through the reference-facing Model.trainIteration with HOST (pinned) batch
+          buffers: H2D of the batch and the D2H loss read are inside the timed region
+  roofline     : the dominant kernel class (the SeqLSTM step), algorithmic FLOP / CUDA-event time
+  cpu_baseline : the oracle ("port" of the reference's CPU path) on a bounded sample, rank 0, N=1 only
+
+`--impl reference` times the reference's own CPU structure (oracle in reference-structure mode, all
+host threads) for the same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "QA-rounds/sec mn-att-ques-im-hist+disc train step"
+ENCODER, DECODER = "mn-att-ques-im-hist", "disc"
+FWD_FLOP_PER_ROUND = 7311261696          # SURVEY.md §8d (C4), forward; training = 3x
+LSTM_STEP_KEYS = ("lstm_step", "lstm_step_bwd")
+
+
+def headline_params(gpuid=0):
+    from visdial_b200.engine import DEFAULT_PARAMS, derive_flags
+    p = dict(DEFAULT_PARAMS)
+    p.update(encoder=ENCODER, decoder=DECODER, vocabSize=10000, imgFeatureSize=512, imgSpatialSize=14, gpuid=gpuid)
+    return derive_flags(p)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1449.3), "hbm": d.get("hbm_gbs", 6579.6), "src": "measured"}
+    return {"bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world <= 1:
+        return x
+    from visdial_b200 import dist as vdist
+    return vdist.max_over_ranks(x)
+
+
+def cpu_oracle_step_time(B, steps, warmup, structure, threads):
+    """Seconds per training step of the oracle on B dialogs (forward, backward, clamp+adam)."""
+    import torch
+    from helpers import torch_batch, torch_params
+    from oracle import philox, visdial_oracle as O
+    from visdial_b200.engine import init_parameters
+    from visdial_b200.synthetic import make_batch
+    torch.set_num_threads(threads)
+    p = headline_params()
+    flat = init_parameters(p, seed=1234)
+    W = torch.from_numpy(flat.copy())
+    state, times = {}, []
+    from helpers import flat_from_named
+    for it in range(warmup + steps):
+        nb = torch_batch(make_batch(p, B, seed=1234 + it))
+        t0 = time.perf_counter()
+        out = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(1234, it + 1), structure=structure), p,
+                                 torch_params(p, W.numpy()), nb)
+        dW = torch.from_numpy(flat_from_named(p, out["grads"]))
+        O.clamp_adam(W, dW, state, 1e-3)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.median(times)), p
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path for the same metric/config (oracle, reference structure: per-timestep
+    addmm, 100 sequential option-LSTM passes, materialised repeatTensor), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.ref_batch
+    sec, p = cpu_oracle_step_time(B, args.steps, min(args.warmup, 1), "reference", threads)
+    val = B * 10 / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "QA-rounds/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4 mn-att-ques-im-hist+disc train step (pool5 14x14x512, 10 rounds, 100 options x 20 tokens, V=10000)",
+                       "global_batch_dialogs": B, "note": "bounded sample of the B=32/GPU workload; per-round throughput"},
+            "cpu_baseline": {"value": val, "unit": "QA-rounds/s", "cores": threads, "kind": "port",
+                             "sample": "%d dialogs (%d QA rounds) per step, oracle reference-structure, torch CPU fp32" % (B, B * 10)},
+            "e2e": {"value": val, "unit": "QA-rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local, world):
+    from visdial_b200 import Batch, Model
+    from visdial_b200 import dist as vdist
+    from visdial_b200.engine import pinned_empty
+    from visdial_b200.synthetic import make_batch
+
+    p = headline_params(gpuid=local)
+    p["batchSize"] = args.batch
+    model = Model(p, seed=1234)                       # same seed on every rank -> identical replicas
+    eng = model.engine
+    if args.math == "fp32":
+        from visdial_b200 import VD_MATH_FP32
+        eng.set_math_mode(VD_MATH_FP32)
+    vdist.attach_engine(eng, rank, world)
+
+    # a few distinct batches per rank, in pinned host memory (weak scaling: B dialogs per GPU)
+    nbatches = 4
+    host_batches = []
+    for i in range(nbatches):
+        nb = make_batch(p, args.batch, seed=1234 + 1000 * rank + i)
+        pinned = {}
+        for k, v in nb.items():
+            if k in ("option_in", "option_out"):
+                continue
+            buf = pinned_empty(v.shape, v.dtype)
+            buf[...] = v
+            pinned[k] = buf
+        host_batches.append(Batch(pinned))
+    dev_batches = [b.to_device(eng) for b in host_batches]
+
+    class Loader:
+        def __init__(self, batches):
+            self.b, self.i = batches, 0
+
+        def getTrainBatch(self, params):
+            self.i += 1
+            return self.b[self.i % len(self.b)]
+
+    def timed(loader, steps, profile):
+        barrier(world)
+        eng.synchronize()
+        eng.profile_reset()
+        eng.profile(profile)
+        l0 = eng.launch_count()
+        t_wall = time.perf_counter()
+        eng.timer_start()
+        for _ in range(steps):
+            model.trainIteration(loader)
+        ms = eng.timer_stop()
+        eng.synchronize()
+        wall = (time.perf_counter() - t_wall) * 1e3
+        barrier(world)
+        eng.profile(False)
+        return ms, wall, eng.launch_count() - l0
+
+    dev_loader, host_loader = Loader(dev_batches), Loader(host_batches)
+    for _ in range(args.warmup):
+        model.trainIteration(dev_loader)
+    model.trainIteration(host_loader)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, launches = timed(dev_loader, args.steps, True)
+    stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS + ("gemm", "gemm_wgrad", "allreduce")}
+    ms_e2e, wall_e2e, _ = timed(host_loader, args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_dev = max_over_ranks(ms_dev, world)
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e), world)     # e2e includes host time: take the wall clock if larger
+    rounds = args.batch * 10 * world * args.steps
+    value = rounds / (ms_dev * 1e-3)
+    e2e = rounds / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0          # TF32 operands: half the bf16 rate
+    n_l = sum(stats[k]["launches"] for k in LSTM_STEP_KEYS)
+    fl = sum(stats[k]["flops"] for k in LSTM_STEP_KEYS)
+    t_ms = sum(stats[k]["ms"] for k in LSTM_STEP_KEYS)
+    achieved = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "lstm_step (recurrent gate GEMM + pointwise, fwd and bwd)",
+                "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                "peak_source": "%s bf16_tflops_sustained / 2 (TF32 operands)" % peaks["src"],
+                "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / max(ms_dev, 1e-9),
+                "traffic": None}
+    step_flops = 3.0 * FWD_FLOP_PER_ROUND * args.batch * 10
+    line = {"metric": METRIC, "value": value, "unit": "QA-rounds/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "C4 mn-att-ques-im-hist+disc train step (pool5 14x14x512, 10 rounds, 100 options x 20 tokens, V=10000)",
+                       "dialogs_per_gpu": args.batch, "global_batch_dialogs": args.batch * world, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (LSTM gates/activations, >10 GB) >> 126 MB L2; 4 rotating input batches"},
+            "e2e": {"value": e2e, "unit": "QA-rounds/s", "h2d_bytes_per_step": host_batches[0].h2d_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "step_tflop_algorithmic": step_flops / 1e12,
+            "step_tflops_achieved": step_flops / (ms_dev / args.steps * 1e-3) / 1e12,
+            "kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in stats.items()},
+            "wall_ms_per_step": wall_dev / args.steps}
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        sec, _ = cpu_oracle_step_time(args.cpu_batch, 1, 1, "reference", threads)
+        line["cpu_baseline"] = {"value": args.cpu_batch * 10 / sec, "unit": "QA-rounds/s", "cores": threads, "kind": "port",
+                                "sample": "%d dialogs (%d QA rounds), 1 warm-up + 1 timed step of the oracle in reference "
+                                          "structure (torch CPU fp32, %d threads)" % (args.cpu_batch, args.cpu_batch * 10, threads)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="dialogs per GPU (BASELINE config 4: 32)")
+    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    rank, local, world = dist_setup(args.gpus)
+    try:
+        run_ours(args, rank, local, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

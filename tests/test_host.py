@@ -1,0 +1,133 @@
+"""Host-side logic that needs no GPU: the synthetic dataloader contract, the plugin loaders, and the
+data-parallel plumbing (world_size-2 gloo: dialog sharding + unique-id broadcast + result gather)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import full_params, small_batch, small_params
+from visdial_b200 import decoders, encoders
+from visdial_b200 import dist as vdist
+from visdial_b200.synthetic import make_batch
+from visdial_b200.utils import processRanks
+
+
+def test_batch_contract_small():
+    p = small_params("mn-att-ques-im-hist", "disc")
+    b = small_batch(p, B=4)
+    B, R, V = 4, 10, p["vocabSize"]
+    q = b["ques_fwd"]
+    assert q.shape[:2] == (B, R) and q.dtype == np.int32
+    # right aligned: once a token appears, no pad follows
+    for row in q.reshape(-1, q.shape[2]):
+        nz = np.nonzero(row)[0]
+        assert len(nz) == 0 or (nz[-1] == len(row) - 1 and np.all(row[nz[0]:] != 0))
+    assert (q.reshape(B * R, -1) != 0).sum(1).min() == 0               # an all-pad round exists
+    assert q.max() <= V - 2
+    h = b["hist"]
+    assert h.shape[:2] == (B, R) and h.shape[2] <= 9
+    assert np.all(h[:, :, -1] != 0)                                     # every round has some history
+    ai, ao = b["answer_in"].reshape(B * R, -1), b["answer_out"].reshape(B * R, -1)
+    assert np.all(ai[:, 0] == V - 1)                                    # <START>
+    assert np.array_equal(ai != 0, ao != 0)                             # aligned lengths
+    L = (ao != 0).sum(1)
+    assert np.all(ao[np.arange(B * R), L - 1] == V)                     # <END> closes every answer
+    o = b["options"]
+    assert o.shape == (B * R, p["numOptions"], 20)
+    for row in o.reshape(-1, 20)[:200]:                                  # left aligned
+        nz = np.nonzero(row)[0]
+        assert len(nz) > 0 and nz[0] == 0 and np.all(row[:nz[-1] + 1] != 0)
+    gt = b["answer_ind"]
+    assert gt.min() >= 1 and gt.max() <= p["numOptions"]
+    assert b["img_feat"].shape == (B, 3, 3, 8)
+
+
+def test_batch_contract_headline_shapes():
+    p = full_params("mn-att-ques-im-hist", "disc")
+    b = make_batch(p, 2, seed=1)
+    assert b["ques_fwd"].shape == (2, 10, 20) and b["hist"].shape == (2, 10, 40)
+    assert b["options"].shape == (20, 100, 20) and b["img_feat"].shape == (2, 14, 14, 512)
+    assert b["answer_in"].shape == (2, 10, 20)
+    p2 = full_params("lf-ques-im-hist", "disc")
+    b2 = make_batch(p2, 2, seed=1)
+    assert b2["img_feat"].shape == (2, 4096)
+    assert np.allclose(np.linalg.norm(b2["img_feat"], axis=1), 1, atol=1e-5)      # L2-normalised fc7
+    assert 40 < b2["hist"].shape[2] <= 300                                        # concatenated history
+    g = make_batch(full_params("lf-ques", "gen"), 1, seed=1, gen_eval=True)
+    assert g["option_in"].shape == g["option_out"].shape and g["option_in"].shape[:3] == (1, 10, 100)
+    assert np.all(g["option_in"][..., 0] == 9999)
+
+
+def test_plugin_loaders():
+    for name in ("lf-ques", "lf-ques-im-hist", "hrea-ques-im-hist", "mn-att-ques-im-hist"):
+        m = encoders.load(name)
+        enc = m.model(small_params(name, "disc"))
+        assert (enc.rnnLayers is None) == name.startswith("mn")        # gModule encoders have no rnnLayers
+    for name in ("disc", "gen"):
+        d = decoders.load(name)
+        assert callable(d.model) and callable(d.forwardConnect) and callable(d.backwardConnect)
+    with pytest.raises(ValueError):
+        decoders.load("nope")
+
+
+def test_process_ranks():
+    m = processRanks(np.array([[1, 2, 10], [100, 5, 1]]), verbose=False)
+    assert m["r@1"] == pytest.approx(2 / 6) and m["r@5"] == pytest.approx(4 / 6) and m["r@10"] == pytest.approx(5 / 6)
+    assert m["meanR"] == pytest.approx(119 / 6) and m["medianR"] == pytest.approx(3.5)
+
+
+def test_shard_dialogs():
+    assert vdist.shard_range(32, 0, 1) == (0, 32)
+    spans = [vdist.shard_range(35, r, 4) for r in range(4)]
+    assert spans[0][0] == 0 and spans[-1][1] == 35
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(3))       # contiguous, never splits a dialog
+    assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    p = small_params("mn-att-ques-im-hist", "disc")
+    b = small_batch(p, B=5)
+    parts = [vdist.shard_batch(b, r, 2, p["maxQuesCount"]) for r in range(2)]
+    assert np.array_equal(np.concatenate([x["options"] for x in parts]), b["options"])
+    assert np.array_equal(np.concatenate([x["ques_fwd"] for x in parts]), b["ques_fwd"])
+    assert np.array_equal(np.concatenate([x["answer_ind"] for x in parts]), b["answer_ind"])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    uid = vdist.broadcast_unique_id(lambda: bytes(range(128)) if rank == 0 else None, rank)
+    p = small_params("mn-att-ques-im-hist", "disc")
+    b = small_batch(p, B=5)
+    mine = vdist.shard_batch(b, rank, world, p["maxQuesCount"])
+    ranks_local = mine["answer_ind"].astype(np.int32)                   # stand-in for per-rank rank output
+    gathered = vdist.gather_ranks(ranks_local, rank, world)
+    t = vdist.max_over_ranks(float(rank + 1))
+    if rank == 0:
+        out.put((uid, gathered.tolist(), b["answer_ind"].tolist(), t))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_plumbing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    uid, gathered, expect, t = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert uid == bytes(range(128))          # rank 0's id reached every rank
+    assert gathered == expect                # rank-ordered concatenation == unsharded order
+    assert t == 2.0                          # timing is the max over ranks

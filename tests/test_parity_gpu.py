@@ -1,0 +1,246 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances: fp32 CUDA-core mode — loss/outputs 2e-5 abs (fp32 re-association only);
+TF32 tensor-core mode — stated per test (TF32 operands have a 10-bit mantissa).  Integer results
+(ranks) are compared exactly."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (CONFIGS, flat_from_named, full_params, seg_slices, small_batch, small_params, torch_batch,
+                     torch_params)
+from oracle import philox
+from oracle import visdial_oracle as O
+from visdial_b200 import VD_MATH_FP32, VD_MATH_TF32, Batch, Engine, Model, init_parameters
+from visdial_b200.synthetic import make_batch
+
+pytestmark = pytest.mark.gpu
+
+SEED, ITER = 11, 3
+
+
+def _assert_close(a, b, atol, rtol, what):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    assert a.shape == b.shape, what
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a - b).max())
+    assert err <= atol + rtol * scale, "%s: max err %.3e (scale %.3e, atol %.1e rtol %.1e)" % (what, err, scale, atol, rtol)
+
+
+def _compare_grads(p, g_eng, g_ref, atol, rtol):
+    sl = seg_slices(p)
+    for name, s in sl.items():
+        _assert_close(g_eng[s], g_ref[name].numpy(), atol, rtol, "grad " + name)
+
+
+def _run_engine(p, flat, nb, mode, training, fused=True):
+    eng = Engine(p)
+    eng.set_math_mode(mode)
+    eng.set_parameters(flat)
+    eng.set_training(training)
+    eng.set_dropout_seed(SEED, ITER)
+    eng.zero_grad()
+    return eng
+
+
+@pytest.mark.parametrize("enc,dec", CONFIGS)
+def test_eval_forward_matches_oracle_fp32(enc, dec):
+    p = small_params(enc, dec)
+    flat = init_parameters(p, seed=3)
+    nb = small_batch(p, B=3)
+    eng = _run_engine(p, flat, nb, VD_MATH_FP32, 0)
+    b = Batch(nb)
+    encOut = eng.encoder_forward(b).numpy()
+    eng.forward_connect()
+    decOut = eng.decoder_forward(b).numpy()
+    loss = eng.criterion_forward(b)
+    ref = O.forward_backward(O.Ctx(train=False), p, torch_params(p, flat), torch_batch(nb), only_forward=True)
+    _assert_close(encOut, ref["encOut"].numpy(), 2e-5, 1e-5, "encOut")
+    _assert_close(decOut, ref["decOut"].numpy(), 5e-5, 1e-5, "decOut")
+    assert abs(loss - ref["loss"]) <= 1e-4 * max(1.0, abs(ref["loss"]))
+    eng.close()
+
+
+@pytest.mark.parametrize("enc,dec", CONFIGS)
+def test_train_forward_backward_matches_oracle_fp32(enc, dec):
+    """Training mode with dropout ON: the oracle is given the engine's Philox masks."""
+    p = small_params(enc, dec)
+    flat = init_parameters(p, seed=3)
+    nb = small_batch(p, B=3)
+    eng = _run_engine(p, flat, nb, VD_MATH_FP32, 1)
+    loss = eng.forward_backward(Batch(nb))
+    g = eng.get_gradients()
+    psite = {O.SITE_FUSION: p["dropout"]}
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(SEED, ITER, psite)), p, torch_params(p, flat),
+                             torch_batch(nb))
+    assert abs(loss - ref["loss"]) <= 1e-4 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
+    _compare_grads(p, g, ref["grads"], 2e-5, 2e-4)
+    eng.close()
+
+
+@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen")])
+def test_model_protocol_equals_fused_path(enc, dec):
+    """Model:forwardBackward driven call-by-call (model.lua:297-337) == vd_forward_backward."""
+    p = small_params(enc, dec)
+    nb = small_batch(p, B=2)
+    m = Model(p, seed=5)
+    m.engine.set_math_mode(VD_MATH_FP32)
+    m.engine.set_dropout_seed(SEED, ITER)
+    m.wrapper.zeroGradParameters()
+    l1 = m.forwardBackward(nb)
+    g1 = m.engine.get_gradients()
+    m.wrapper.zeroGradParameters()
+    l2 = m.engine.forward_backward(Batch(nb))
+    g2 = m.engine.get_gradients()
+    assert l1 == pytest.approx(l2, rel=1e-6)
+    _assert_close(g1, g2, 1e-6, 1e-4, "fused vs protocol grads")   # atomics re-order fp32 sums
+    m.engine.close()
+
+
+@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("lf-ques", "gen")])
+def test_train_iteration_adam_matches_oracle(enc, dec):
+    """Model:trainIteration = zeroGrad, fwd/bwd, clamp(-5,5), adam, lr decay (model.lua:66-106)."""
+    p = small_params(enc, dec)
+    nb = small_batch(p, B=2)
+
+    class DL:
+        def getTrainBatch(self, params):
+            return nb
+    m = Model(p, seed=5)
+    m.engine.set_math_mode(VD_MATH_FP32)
+    flat0 = m.engine.get_parameters()
+    W = torch.from_numpy(flat0.copy())
+    state = {}
+    lr = p["learningRate"]
+    for it in range(1, 4):
+        m.trainIteration(DL())
+        psite = {O.SITE_FUSION: p["dropout"]}
+        ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(1234, it, psite)), p,
+                                 torch_params(p, W.numpy()), torch_batch(nb))
+        dW = torch.from_numpy(flat_from_named(p, ref["grads"]))
+        O.clamp_adam(W, dW, state, lr)
+        W[:p["embedSize"]] = 0         # pad row is re-zeroed at the next forward (LookupTableMaskZero)
+        lr = O.decay_lr(lr, p)
+        got = m.engine.get_parameters()
+        got[:p["embedSize"]] = 0
+        # Adam normalises the step to ~lr: compare in units of lr
+        assert float(np.abs(got - W.numpy()).max()) < 0.05 * p["learningRate"], it
+    assert m.optims["learningRate"] == pytest.approx(lr)
+    m.engine.close()
+
+
+@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("lf-ques-im-hist", "disc"),
+                                     ("lf-ques", "gen"), ("hrea-ques-im-hist", "gen")])
+def test_retrieve_ranks_bit_exact(enc, dec):
+    p = small_params(enc, dec)
+    flat = init_parameters(p, seed=3)
+    nb = small_batch(p, B=3, gen_eval=(dec == "gen"))
+    eng = _run_engine(p, flat, nb, VD_MATH_FP32, 1)
+    r_gt = eng.retrieve(Batch(nb), use_gt=True)
+    r_all = eng.retrieve(Batch(nb), use_gt=False)
+    P = torch_params(p, flat)
+    tb = torch_batch(nb)
+    ref_gt = O.retrieve_batch(O.Ctx(), p, P, tb, use_gt=True).numpy()
+    ref_all = O.retrieve_batch(O.Ctx(), p, P, tb, use_gt=False).numpy()
+    assert np.array_equal(r_gt, ref_gt)
+    assert np.array_equal(r_all, ref_all)
+    eng.close()
+
+
+def test_rank_kernel_ties_and_permutation():
+    p = small_params("lf-ques", "disc", numOptions=100)
+    eng = Engine(p)
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal((64, 100)).astype(np.float32)
+    s[:, 10] = s[:, 3]            # exact ties: lower index wins
+    s[5] = 0.0                    # a fully tied row ranks 1..100 in index order
+    from visdial_b200 import engine as E
+    from visdial_b200._lib import check
+    dev_s, dev_r = C.c_void_p(), C.c_void_p()
+    lib = eng.lib
+    # use the parameter gradient buffer as scratch device memory
+    w, dw = eng.param_buffers()
+    check(lib.vd_memcpy_h2d(eng.h, dw, s.ctypes.data, s.nbytes))
+    ranks_dev = dw + s.nbytes
+    check(lib.vd_compute_ranks(eng.h, dw, 64, None, ranks_dev))
+    out = np.empty((64, 100), dtype=np.int32)
+    check(lib.vd_memcpy_d2h(eng.h, out.ctypes.data, ranks_dev, out.nbytes))
+    ref = O.compute_ranks(torch.from_numpy(s)).numpy()
+    assert np.array_equal(out, ref)
+    assert out[5].tolist() == list(range(1, 101))
+    assert all(sorted(r.tolist()) == list(range(1, 101)) for r in out)
+    eng.close()
+
+
+def test_headline_shapes_against_oracle_fp32():
+    """mn-att-ques-im-hist + disc at the reference's real layer sizes (E=300, H=512, pool5 14x14x512,
+    100 options x 20 tokens, V=10000), B=2 so the oracle finishes in seconds."""
+    p = full_params("mn-att-ques-im-hist", "disc")
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 2, seed=5)
+    eng = _run_engine(p, flat, nb, VD_MATH_FP32, 1)
+    loss = eng.forward_backward(Batch(nb))
+    g = eng.get_gradients()
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(SEED, ITER), structure="batched"), p,
+                             torch_params(p, flat), torch_batch(nb))
+    assert abs(loss - ref["loss"]) <= 2e-4 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
+    _compare_grads(p, g, ref["grads"], 1e-5, 2e-3)
+    ranks = eng.retrieve(Batch(nb), use_gt=False)
+    ref_r = O.retrieve_batch(O.Ctx(structure="batched"), p, torch_params(p, flat), torch_batch(nb), use_gt=False).numpy()
+    # ranks are exact wherever the oracle's score gap to the neighbours exceeds the fp32 noise floor
+    sc = O.forward_backward(O.Ctx(structure="batched"), p, torch_params(p, flat), torch_batch(nb), only_forward=True)["decOut"].numpy()
+    srt = np.sort(sc, 1)
+    min_gap = np.diff(srt, axis=1).min(1)
+    ok = min_gap > 1e-4
+    assert ok.sum() >= 0.8 * len(ok)
+    assert np.array_equal(ranks[ok], ref_r[ok])
+    eng.close()
+
+
+def test_full_size_properties_baseline_batch():
+    """BASELINE config 4 at B=32 (N=320 rounds): size-independent properties."""
+    p = full_params("mn-att-ques-im-hist", "disc")
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 32, seed=5)
+    eng = Engine(p)
+    eng.set_parameters(flat)
+    eng.set_training(1)
+    eng.set_dropout_seed(SEED, ITER)
+    eng.zero_grad()
+    l1 = eng.forward_backward(Batch(nb))
+    g1 = eng.get_gradients()
+    assert np.isfinite(l1) and abs(l1 - np.log(100)) < 1.0          # random init: loss ~ ln(100)
+    assert np.isfinite(g1).all() and np.abs(g1).max() > 0
+    # linearity of gradient accumulation: a second backward without zeroGrad doubles dW
+    l2 = eng.forward_backward(Batch(nb))
+    g2 = eng.get_gradients()
+    assert l2 == pytest.approx(l1, rel=1e-5)
+    _assert_close(g2, 2 * g1, 1e-6, 2e-3, "accumulated grads")
+    # ranks: every row is a permutation of 1..100; the rank of the gt equals the full-rank entry
+    r_all = eng.retrieve(Batch(nb), use_gt=False)
+    r_gt = eng.retrieve(Batch(nb), use_gt=True)
+    assert (np.sort(r_all, 1) == np.arange(1, 101)[None, :]).all()
+    assert np.array_equal(r_gt, r_all[np.arange(320), nb["answer_ind"] - 1])
+    # eval is idempotent and independent of the dropout seed
+    eng.set_dropout_seed(99, 99)
+    assert np.array_equal(eng.retrieve(Batch(nb), use_gt=False), r_all)
+    eng.close()
+
+
+def test_errors_are_loud():
+    from visdial_b200 import VdError
+    p = small_params("mn-att-ques-im-hist", "disc")
+    eng = Engine(p)
+    nb = small_batch(p, B=2)
+    with pytest.raises(VdError):                       # backward before forward
+        eng.decoder_backward(Batch(nb))
+    bad = dict(nb)
+    bad.pop("hist")
+    with pytest.raises(VdError):                       # encoder needs history
+        eng.encoder_forward(Batch(bad))
+    eng.set_training(0)
+    eng.forward_backward(Batch(nb), only_forward=True)
+    with pytest.raises(VdError):                       # no backward from an eval-mode forward
+        eng.criterion_backward(Batch(nb)) or eng.decoder_backward(Batch(nb))
+    eng.close()

@@ -1,0 +1,263 @@
+// extern "C" boundary (include/visdial_b200.h).  Exceptions stop here: every entry returns an error code and
+// leaves the message in a thread-local buffer (vd_last_error).
+#include "engine.h"
+#include <string.h>
+
+namespace vd {
+void comm_unique_id(void* out);
+void comm_init(Engine* e, const void* idbytes, int rank, int world);
+void comm_destroy(Engine* e);
+}  // namespace vd
+
+using vd::Engine;
+
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+#define VD_TRY(body)                                            \
+  try {                                                         \
+    body;                                                       \
+    return VD_OK;                                               \
+  } catch (const vd::CudaError& ex) {                           \
+    return fail(ex.code, ex.what());                            \
+  } catch (const std::exception& ex) {                          \
+    return fail(VD_E_CUDA, ex.what());                          \
+  } catch (...) {                                               \
+    return fail(VD_E_CUDA, "unknown error");                    \
+  }
+
+struct vd_engine { Engine* e; };
+#define ENG(h) ((h) ? (h)->e : (throw vd::CudaError(VD_E_BADARG, "engine handle is null"), (Engine*)nullptr))
+#define NOTNULL(p) VD_REQUIRE((p) != nullptr, VD_E_BADARG, "null output pointer")
+
+extern "C" {
+
+const char* vd_last_error(void) { return g_err; }
+
+int vd_layout_count(const vd_params* p, int32_t* n_segments, int64_t* n_params) {
+  VD_TRY({
+    vd::Layout l = vd::build_layout(vd::parse_cfg(p));
+    if (n_segments) *n_segments = (int32_t)l.segs.size();
+    if (n_params) *n_params = l.total;
+  })
+}
+
+int vd_layout_segment(const vd_params* p, int32_t idx, char* name, int32_t name_cap, int64_t* offset, int64_t* rows,
+                      int64_t* cols, int32_t* init_kind, int64_t* fan_in) {
+  VD_TRY({
+    vd::Layout l = vd::build_layout(vd::parse_cfg(p));
+    VD_REQUIRE(idx >= 0 && idx < (int)l.segs.size(), VD_E_BADARG, "segment index out of range");
+    const vd::Seg& s = l.segs[idx];
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", s.name.c_str());
+    if (offset) *offset = s.off;
+    if (rows) *rows = s.rows;
+    if (cols) *cols = s.cols;
+    if (init_kind) *init_kind = s.init;
+    if (fan_in) *fan_in = s.fan_in;
+  })
+}
+
+int vd_create(const vd_params* p, vd_engine** out) {
+  VD_TRY({
+    NOTNULL(out);
+    *out = nullptr;
+    Engine* e = new Engine(p);
+    vd_engine* h = new vd_engine;
+    h->e = e;
+    *out = h;
+  })
+}
+
+int vd_destroy(vd_engine* h) {
+  VD_TRY({
+    if (h) { vd::comm_destroy(h->e); delete h->e; delete h; }
+  })
+}
+
+int vd_num_params(vd_engine* h, int64_t* n) { VD_TRY({ NOTNULL(n); *n = ENG(h)->nparams; }) }
+int vd_param_buffers(vd_engine* h, float** W, float** dW) {
+  VD_TRY({ Engine* e = ENG(h); if (W) *W = e->W; if (dW) *dW = e->dW; })
+}
+int vd_optim_buffers(vd_engine* h, float** m, float** v, int64_t* t) {
+  VD_TRY({ Engine* e = ENG(h); if (m) *m = e->m; if (v) *v = e->v; if (t) *t = e->adam_t; })
+}
+int vd_set_parameters(vd_engine* h, const float* src, int64_t n) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(src && n == e->nparams, VD_E_SHAPE, "vd_set_parameters: n must equal vd_num_params");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    VD_CUDA_CHECK(cudaMemcpyAsync(e->W, src, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->cx.stream));
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+  })
+}
+static void copy_out(Engine* e, float* dst, const float* src, int64_t n) {
+  VD_REQUIRE(dst && n == e->nparams, VD_E_SHAPE, "n must equal vd_num_params");
+  VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+  VD_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->cx.stream));
+  VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+}
+int vd_get_parameters(vd_engine* h, float* dst, int64_t n) { VD_TRY({ Engine* e = ENG(h); copy_out(e, dst, e->W, n); }) }
+int vd_get_gradients(vd_engine* h, float* dst, int64_t n) { VD_TRY({ Engine* e = ENG(h); copy_out(e, dst, e->dW, n); }) }
+int vd_zero_grad(vd_engine* h) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    VD_CUDA_CHECK(cudaMemsetAsync(e->dW, 0, (size_t)e->nparams * sizeof(float), e->cx.stream));
+  })
+}
+
+int vd_set_training(vd_engine* h, int32_t training) {
+  VD_TRY({ VD_REQUIRE(training >= 0 && training <= 2, VD_E_BADARG, "training must be 0, 1 or 2"); ENG(h)->training = training; })
+}
+int vd_set_dropout_seed(vd_engine* h, uint64_t seed, uint64_t iteration) {
+  VD_TRY({ Engine* e = ENG(h); e->drop_seed = seed; e->drop_iter = iteration; })
+}
+int vd_set_math_mode(vd_engine* h, int32_t mode) {
+  VD_TRY({ VD_REQUIRE(mode == VD_MATH_TF32 || mode == VD_MATH_FP32, VD_E_BADARG, "unknown math mode"); ENG(h)->math_mode = mode; })
+}
+
+int vd_encoder_forward(vd_engine* h, const vd_batch* b, const float** encOut) {
+  VD_TRY({ Engine* e = ENG(h); e->encoder_forward(b); if (encOut) *encOut = e->encOut; })
+}
+int vd_forward_connect(vd_engine* h) { VD_TRY({ ENG(h)->forward_connect(); }) }
+int vd_decoder_forward(vd_engine* h, const vd_batch* b, const float** decOut) {
+  VD_TRY({
+    (void)b;
+    Engine* e = ENG(h);
+    e->decoder_forward();
+    if (decOut) *decOut = e->cfg.dec == vd::DEC_DISC ? e->scores : e->logp;
+  })
+}
+int vd_criterion_forward(vd_engine* h, const vd_batch* b, float* loss) {
+  VD_TRY({ (void)b; NOTNULL(loss); *loss = ENG(h)->criterion_forward(); })
+}
+int vd_criterion_backward(vd_engine* h, const vd_batch* b) { VD_TRY({ (void)b; ENG(h)->criterion_backward(); }) }
+int vd_decoder_backward(vd_engine* h, const vd_batch* b) { VD_TRY({ (void)b; ENG(h)->decoder_backward(); }) }
+int vd_backward_connect(vd_engine* h, const float** gradEncOut) {
+  VD_TRY({ const float* g = ENG(h)->backward_connect(); if (gradEncOut) *gradEncOut = g; })
+}
+int vd_encoder_backward(vd_engine* h, const vd_batch* b, const float* gradEncOut) {
+  VD_TRY({ (void)b; ENG(h)->encoder_backward(gradEncOut); })
+}
+
+int vd_forward_backward(vd_engine* h, const vd_batch* b, int32_t only_forward, float* loss) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    e->encoder_forward(b);
+    e->forward_connect();
+    e->decoder_forward();
+    float l = e->criterion_forward();
+    if (loss) *loss = l;
+    if (!only_forward) {
+      e->criterion_backward();
+      e->decoder_backward();
+      const float* g = e->backward_connect();
+      e->encoder_backward(g);
+    }
+  })
+}
+
+int vd_retrieve(vd_engine* h, const vd_batch* b, int32_t use_gt, int32_t* ranks_host) {
+  VD_TRY({ ENG(h)->retrieve(b, use_gt, ranks_host); })
+}
+int vd_compute_ranks(vd_engine* h, const float* scores_dev, int32_t n_rows, const int32_t* gt_dev, int32_t* ranks_dev) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(scores_dev && ranks_dev && n_rows >= 0, VD_E_BADARG, "null scores / ranks");
+    vd::rank_rows(e->cx, scores_dev, gt_dev, ranks_dev, n_rows, e->cfg.K);
+  })
+}
+int vd_gen_option_lhood(vd_engine* h, const vd_batch* b, const float** lhood_dev) {
+  VD_TRY({ (void)b; Engine* e = ENG(h); e->gen_option_lhood(); if (lhood_dev) *lhood_dev = e->lhood; })
+}
+
+int vd_clamp_adam_step(vd_engine* h, float lr) { VD_TRY({ ENG(h)->clamp_adam_step(lr); }) }
+
+int vd_comm_unique_id(void* id_out) { VD_TRY({ NOTNULL(id_out); vd::comm_unique_id(id_out); }) }
+int vd_comm_init(vd_engine* h, const void* id, int32_t rank, int32_t world) {
+  VD_TRY({ VD_REQUIRE(id != nullptr || world == 1, VD_E_BADARG, "id is null"); vd::comm_init(ENG(h), id, rank, world); })
+}
+int vd_comm_allreduce_grads(vd_engine* h) { VD_TRY({ ENG(h)->allreduce_grads(); }) }
+
+int vd_memcpy_d2h(vd_engine* h, void* dst, const void* src, size_t bytes) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(dst && src, VD_E_BADARG, "null pointer");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    VD_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->cx.stream));
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+  })
+}
+int vd_memcpy_h2d(vd_engine* h, void* dst, const void* src, size_t bytes) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(dst && src, VD_E_BADARG, "null pointer");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    VD_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->cx.stream));
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+  })
+}
+int vd_host_alloc(void** ptr, size_t bytes) {
+  VD_TRY({ NOTNULL(ptr); *ptr = nullptr; VD_CUDA_CHECK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault)); })
+}
+int vd_host_free(void* ptr) { VD_TRY({ if (ptr) VD_CUDA_CHECK(cudaFreeHost(ptr)); }) }
+int vd_device_alloc(vd_engine* h, void** ptr, size_t bytes) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    NOTNULL(ptr);
+    *ptr = nullptr;
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    VD_CUDA_CHECK(cudaMalloc(ptr, bytes ? bytes : 1));
+  })
+}
+int vd_device_free(vd_engine* h, void* ptr) {
+  VD_TRY({ Engine* e = ENG(h); VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid)); if (ptr) VD_CUDA_CHECK(cudaFree(ptr)); })
+}
+int vd_synchronize(vd_engine* h) { VD_TRY({ VD_CUDA_CHECK(cudaStreamSynchronize(ENG(h)->cx.stream)); }) }
+int vd_stream(vd_engine* h, void** s) { VD_TRY({ NOTNULL(s); *s = (void*)ENG(h)->cx.stream; }) }
+int vd_timer_start(vd_engine* h) { VD_TRY({ Engine* e = ENG(h); VD_CUDA_CHECK(cudaEventRecord(e->t0, e->cx.stream)); }) }
+int vd_timer_stop(vd_engine* h, float* ms) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    NOTNULL(ms);
+    VD_CUDA_CHECK(cudaEventRecord(e->t1, e->cx.stream));
+    VD_CUDA_CHECK(cudaEventSynchronize(e->t1));
+    VD_CUDA_CHECK(cudaEventElapsedTime(ms, e->t0, e->t1));
+  })
+}
+int vd_profile_enable(vd_engine* h, int32_t on) { VD_TRY({ ENG(h)->cx.profiling = on != 0; }) }
+int vd_profile_reset(vd_engine* h) {
+  VD_TRY({ Engine* e = ENG(h); e->cx.collect(); e->cx.stats.clear(); e->cx.launches = 0; })
+}
+int vd_launch_count(vd_engine* h, int64_t* n) { VD_TRY({ NOTNULL(n); *n = ENG(h)->cx.launches; }) }
+int vd_kernel_stats(vd_engine* h, const char* name, int64_t* launches, double* total_ms, double* total_flops,
+                    double* total_bytes) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(name != nullptr, VD_E_BADARG, "name is null");
+    e->cx.collect();
+    auto it = e->cx.stats.find(name);
+    vd::KStat z;
+    const vd::KStat& s = it == e->cx.stats.end() ? z : it->second;
+    if (launches) *launches = s.launches;
+    if (total_ms) *total_ms = s.ms;
+    if (total_flops) *total_flops = s.flops;
+    if (total_bytes) *total_bytes = s.bytes;
+  })
+}
+int vd_flush_l2(vd_engine* h) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    if (!e->flush_buf) {
+      e->flush_n = (int64_t)(192u << 20) / 4;      // 192 MiB > 126 MB L2
+      VD_CUDA_CHECK(cudaMalloc((void**)&e->flush_buf, (size_t)e->flush_n * 4));
+    }
+    vd::fill_l2_flush(e->cx, e->flush_buf, e->flush_n);
+  })
+}
+
+}  // extern "C"

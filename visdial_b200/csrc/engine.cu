@@ -1,0 +1,777 @@
+// Engine orchestration: replaces Model:forwardBackward / retrieveBatch (/root/reference/model.lua:249-430)
+// and the nn graphs of encoders/*.lua + decoders/*.lua for the four configured encoders.
+#include "engine.h"
+#include <string.h>
+#include <math.h>
+
+namespace vd {
+
+// ------------------------------------------------------------------------------------------------
+// config + parameter layout
+// ------------------------------------------------------------------------------------------------
+Cfg parse_cfg(const vd_params* p) {
+  VD_REQUIRE(p && p->encoder && p->decoder, VD_E_BADARG, "params / encoder / decoder is null");
+  Cfg c;
+  c.encoder = p->encoder; c.decoder = p->decoder;
+  if (c.encoder == "lf-ques") c.enc = ENC_LF_QUES;
+  else if (c.encoder == "lf-ques-im-hist") c.enc = ENC_LF_QIH;
+  else if (c.encoder == "hrea-ques-im-hist") c.enc = ENC_HREA;
+  else if (c.encoder == "mn-att-ques-im-hist") c.enc = ENC_MN_ATT;
+  else VD_REQUIRE(false, VD_E_BADARG, "unknown encoder (lf-ques | lf-ques-im-hist | hrea-ques-im-hist | mn-att-ques-im-hist)");
+  if (c.decoder == "disc") c.dec = DEC_DISC;
+  else if (c.decoder == "gen") c.dec = DEC_GEN;
+  else VD_REQUIRE(false, VD_E_BADARG, "unknown decoder (disc | gen)");
+  c.V = p->vocabSize; c.E = p->embedSize; c.H = p->rnnHiddenSize; c.L = p->numLayers; c.F = p->imgFeatureSize;
+  c.S = p->imgSpatialSize; c.IE = p->imgEmbedSize; c.Cm = p->commonEmbeddingSize; c.hops = p->numAttentionLayers;
+  c.R = p->maxQuesCount; c.K = p->numOptions; c.dropout = p->dropout; c.gpuid = p->gpuid;
+  // opts.lua:55-59,62
+  c.useHist = c.encoder.find("hist") != std::string::npos;
+  c.useIm = c.encoder.find("im") != std::string::npos;
+  c.att = c.encoder.find("att") != std::string::npos;
+  VD_REQUIRE(c.V > 2 && c.E > 0 && c.H > 0, VD_E_BADARG, "vocabSize / embedSize / rnnHiddenSize must be positive");
+  VD_REQUIRE(c.L == 2, VD_E_BADARG, "numLayers must be 2");
+  VD_REQUIRE(c.E % 4 == 0 && c.H % 32 == 0 && c.IE % 4 == 0 && c.Cm % 4 == 0 && c.F % 4 == 0, VD_E_BADARG,
+             "embedSize/imgEmbedSize/commonEmbeddingSize/imgFeatureSize must be multiples of 4, rnnHiddenSize of 32");
+  VD_REQUIRE(c.R >= 1 && c.R <= 32 && c.K >= 1 && c.K <= 1024 && c.hops >= 1, VD_E_BADARG, "maxQuesCount/numOptions/numAttentionLayers out of range");
+  VD_REQUIRE(c.dropout >= 0.f && c.dropout < 1.f, VD_E_BADARG, "dropout must be in [0,1)");
+  return c;
+}
+
+int Layout::find(const std::string& name) const {
+  for (size_t i = 0; i < segs.size(); ++i)
+    if (segs[i].name == name) return (int)i;
+  return -1;
+}
+
+static void add_seg(Layout& l, const std::string& name, int64_t rows, int64_t cols, int init, int64_t fan_in) {
+  Seg s; s.name = name; s.rows = rows; s.cols = cols; s.init = init; s.fan_in = fan_in; s.off = l.total;
+  l.segs.push_back(s);
+  l.total += (rows * cols + 31) / 32 * 32;       // every segment starts 128-byte aligned
+}
+static void add_lstm(Layout& l, const std::string& n, int D, int H) {
+  add_seg(l, n + ".weight", D + H, 4 * H, VD_INIT_LSTM_W, D + H);
+  add_seg(l, n + ".bias", 1, 4 * H, VD_INIT_LSTM_B, D + H);
+}
+static void add_linear(Layout& l, const std::string& n, int out, int in) {
+  add_seg(l, n + ".weight", out, in, VD_INIT_LINEAR_W, in);
+  add_seg(l, n + ".bias", 1, out, VD_INIT_LINEAR_B, in);
+}
+
+Layout build_layout(const Cfg& c) {
+  Layout l;
+  add_seg(l, "wordEmbed.weight", c.V + 1, c.E, VD_INIT_EMBED, 0);
+  switch (c.enc) {
+    case ENC_LF_QUES:
+      add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+      add_linear(l, "fusion", c.H, c.H);
+      break;
+    case ENC_LF_QIH:
+      add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+      add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
+      add_linear(l, "fusion", c.H, 2 * c.H + c.F);
+      break;
+    case ENC_HREA:
+      add_linear(l, "img.embed", c.IE, c.F);
+      add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
+      add_lstm(l, "ques.lstm1", c.E + c.IE, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+      add_linear(l, "att.q", 1, c.H); add_linear(l, "att.h", 1, c.H);
+      add_lstm(l, "dialog.lstm", 2 * c.H, c.H);
+      break;
+    case ENC_MN_ATT:
+      add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
+      add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+      add_linear(l, "mn.fact", c.H, c.H); add_linear(l, "mn.query", c.H, c.H);
+      add_linear(l, "san.img", c.H, c.F);
+      for (int h = 1; h <= c.hops; ++h) {
+        std::string p = "san.hop" + std::to_string(h) + ".";
+        add_linear(l, p + "img_common", c.Cm, c.H);
+        add_linear(l, p + "ques_common", c.Cm, c.H);
+        add_linear(l, p + "score", 1, c.Cm);
+      }
+      add_linear(l, "san.out", c.H, c.H);
+      break;
+  }
+  if (c.dec == DEC_DISC) {
+    add_lstm(l, "opt.lstm", c.E, c.H);
+  } else {
+    add_lstm(l, "dec.lstm1", c.E, c.H); add_lstm(l, "dec.lstm2", c.H, c.H);
+    add_linear(l, "dec.out", c.V, c.H);
+  }
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------------
+void* Arena::alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  while (cur < chunks.size()) {
+    Chunk& c = chunks[cur];
+    if (c.used + bytes <= c.cap) { void* p = c.p + c.used; c.used += bytes; return p; }
+    ++cur;
+  }
+  Chunk c; c.cap = std::max<size_t>(bytes, (size_t)256 << 20); c.used = bytes;
+  VD_CUDA_CHECK(cudaMalloc((void**)&c.p, c.cap));
+  chunks.push_back(c);
+  cur = chunks.size() - 1;
+  return c.p;
+}
+void Arena::reset() { for (auto& c : chunks) c.used = 0; cur = 0; }
+void Arena::release() { for (auto& c : chunks) cudaFree(c.p); chunks.clear(); cur = 0; }
+
+void* GrowBuf::ensure(size_t bytes) {
+  if (bytes > cap) {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    VD_CUDA_CHECK(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  return p;
+}
+void GrowBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(const vd_params* p) {
+  cfg = parse_cfg(p);
+  lay = build_layout(cfg);
+  nparams = lay.total;
+  int ndev = 0;
+  VD_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  VD_REQUIRE(cfg.gpuid >= 0 && cfg.gpuid < ndev, VD_E_BADARG, "gpuid out of range");
+  VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  cudaDeviceProp prop;
+  VD_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg.gpuid));
+  VD_REQUIRE(prop.major == 10, VD_E_CUDA, "visdial_b200 is built for sm_100a (B200) only");
+  cx.sm_count = prop.multiProcessorCount;
+  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+  size_t bytes = (size_t)nparams * sizeof(float);
+  VD_CUDA_CHECK(cudaMalloc((void**)&W, bytes));
+  VD_CUDA_CHECK(cudaMalloc((void**)&dW, bytes));
+  VD_CUDA_CHECK(cudaMalloc((void**)&m, bytes));
+  VD_CUDA_CHECK(cudaMalloc((void**)&v, bytes));
+  VD_CUDA_CHECK(cudaMalloc((void**)&Wt, bytes));
+  VD_CUDA_CHECK(cudaMemsetAsync(W, 0, bytes, cx.stream));
+  VD_CUDA_CHECK(cudaMemsetAsync(dW, 0, bytes, cx.stream));
+  VD_CUDA_CHECK(cudaMemsetAsync(m, 0, bytes, cx.stream));
+  VD_CUDA_CHECK(cudaMemsetAsync(v, 0, bytes, cx.stream));
+  VD_CUDA_CHECK(cudaMemsetAsync(Wt, 0, bytes, cx.stream));
+  VD_CUDA_CHECK(cudaMalloc((void**)&scalars_dev, 64 * sizeof(float)));
+  // table of 2-D weight segments that get a transposed shadow copy
+  std::vector<int64_t> tab;
+  for (auto& s : lay.segs) {
+    if (s.init == VD_INIT_LSTM_W || s.init == VD_INIT_LINEAR_W) {
+      tab.push_back(s.off); tab.push_back(s.rows); tab.push_back(s.cols);
+      max2d = std::max(max2d, s.rows * s.cols);
+    }
+  }
+  nseg2d = (int)tab.size() / 3;
+  VD_CUDA_CHECK(cudaMalloc((void**)&segtab_dev, tab.size() * sizeof(int64_t)));
+  VD_CUDA_CHECK(cudaMemcpyAsync(segtab_dev, tab.data(), tab.size() * sizeof(int64_t), cudaMemcpyHostToDevice, cx.stream));
+  VD_CUDA_CHECK(cudaStreamSynchronize(cx.stream));
+  VD_CUDA_CHECK(cudaEventCreate(&t0));
+  VD_CUDA_CHECK(cudaEventCreate(&t1));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(cfg.gpuid);
+  cudaStreamSynchronize(cx.stream);
+  arena.release();
+  for (auto& g : stage) g.release();
+  cudaFree(W); cudaFree(dW); cudaFree(m); cudaFree(v); cudaFree(Wt); cudaFree(scalars_dev); cudaFree(segtab_dev);
+  if (flush_buf) cudaFree(flush_buf);
+  cx.collect();
+  for (auto e : cx.free_events) cudaEventDestroy(e);
+  if (t0) cudaEventDestroy(t0);
+  if (t1) cudaEventDestroy(t1);
+  cudaStreamDestroy(cx.stream);
+}
+
+int Engine::seg(const char* name) const {
+  int i = lay.find(name);
+  VD_REQUIRE(i >= 0, VD_E_STATE, name);
+  return i;
+}
+
+DropCfg Engine::dropcfg(float p) const {
+  DropCfg d;
+  d.seed_lo = (uint32_t)drop_seed; d.seed_hi = (uint32_t)(drop_seed >> 32); d.iter = (uint32_t)drop_iter;
+  if (training == 1 && p > 0.f) {
+    double t = (double)p * 4294967296.0;
+    d.thresh = (uint32_t)std::min(t, 4294967295.0);
+    d.scale = 1.f / (1.f - p);
+  } else { d.thresh = 0; d.scale = 1.f; }
+  return d;
+}
+
+void Engine::gemm_tn(int M, int N, int K, const float* A, int64_t lda, const int32_t* gather, const float* B, int64_t ldb,
+                     float* C, int64_t ldc, float beta, const float* bias, int act) {
+  LaunchCtx::Scope sc(&cx, "gemm", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N));
+  if (math_mode == VD_MATH_TF32 && gemm_tn_tc(cx, M, N, K, A, lda, gather, B, ldb, C, ldc, beta, bias, act)) return;
+  gemm_tn_simt(cx, M, N, K, A, lda, gather, B, ldb, C, ldc, beta, bias, act);
+}
+void Engine::gemm_atb(int M, int N, int64_t K, const float* A, int64_t lda, const int32_t* gather, const float* B,
+                      int64_t ldb, float* C, int64_t ldc) {
+  LaunchCtx::Scope sc(&cx, "gemm_wgrad", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N));
+  if (math_mode == VD_MATH_TF32 && gemm_atb_tc(cx, M, N, K, A, lda, gather, B, ldb, C, ldc)) return;
+  gemm_atb_simt(cx, M, N, K, A, lda, gather, B, ldb, C, ldc);
+}
+
+void Engine::linear_fwd(int wseg, const float* x, int64_t rows, float* y, int act) {
+  const Seg& s = lay.segs[wseg];
+  gemm_tn((int)rows, (int)s.rows, (int)s.cols, x, s.cols, nullptr, Wp(wseg), s.cols, y, s.rows, 0.f, Wp(wseg + 1), act);
+}
+void Engine::linear_bwd(int wseg, const float* x, const float* dy, int64_t rows, float* dx, float beta_dx) {
+  const Seg& s = lay.segs[wseg];
+  int out = (int)s.rows, in = (int)s.cols;
+  gemm_atb(out, in, rows, dy, out, nullptr, x, in, dWp(wseg), in);
+  colsum_add(cx, dWp(wseg + 1), dy, rows, out, out);
+  if (dx) gemm_tn((int)rows, in, out, dy, out, nullptr, Wtp(wseg), out, dx, in, beta_dx, nullptr, 0);
+}
+
+void Engine::refresh_shadows() {
+  // LookupTableMaskZero.updateOutput zeroes the pad row at every forward [upstream rnn]
+  VD_CUDA_CHECK(cudaMemsetAsync(W, 0, (size_t)cfg.E * sizeof(float), cx.stream));
+  transpose_segments(cx, W, Wt, segtab_dev, nseg2d, max2d);
+}
+
+void Engine::stage_batch(const vd_batch* b) {
+  VD_REQUIRE(b != nullptr, VD_E_BADARG, "batch is null");
+  VD_REQUIRE(b->B > 0, VD_E_SHAPE, "batch B must be > 0");
+  db = DevBatch();
+  db.B = b->B; db.N = (int64_t)b->B * cfg.R;
+  db.Tq = b->Tq; db.Th = b->Th; db.Ta = b->Ta; db.To = b->To;
+  VD_REQUIRE(b->ques_fwd && b->Tq > 0, VD_E_SHAPE, "ques_fwd / Tq missing");
+  if (cfg.useHist) VD_REQUIRE(b->hist && b->Th > 0, VD_E_SHAPE, "encoder uses history: hist / Th missing");
+  if (cfg.useIm) VD_REQUIRE(b->img_feat, VD_E_SHAPE, "encoder uses the image: img_feat missing");
+  int64_t img_elems = cfg.att ? (int64_t)b->B * cfg.S * cfg.S * cfg.F : (int64_t)b->B * cfg.F;
+  struct Item { const void* src; size_t bytes; const void** dst; } items[9] = {
+      {b->ques_fwd, (size_t)db.N * b->Tq * 4, (const void**)&db.ques},
+      {cfg.useHist ? b->hist : nullptr, (size_t)db.N * b->Th * 4, (const void**)&db.hist},
+      {cfg.useIm ? b->img_feat : nullptr, (size_t)img_elems * 4, (const void**)&db.img},
+      {b->options, (size_t)db.N * cfg.K * b->To * 4, (const void**)&db.options},
+      {b->answer_ind, (size_t)db.N * 4, (const void**)&db.answer_ind},
+      {b->answer_in, (size_t)db.N * b->Ta * 4, (const void**)&db.answer_in},
+      {b->answer_out, (size_t)db.N * b->Ta * 4, (const void**)&db.answer_out},
+      {b->option_in, (size_t)db.N * cfg.K * b->To * 4, (const void**)&db.option_in},
+      {b->option_out, (size_t)db.N * cfg.K * b->To * 4, (const void**)&db.option_out}};
+  for (int i = 0; i < 9; ++i) {
+    if (!items[i].src || items[i].bytes == 0) { *items[i].dst = nullptr; continue; }
+    if (b->on_device) { *items[i].dst = items[i].src; continue; }
+    void* d = stage[i].ensure(items[i].bytes);
+    VD_CUDA_CHECK(cudaMemcpyAsync(d, items[i].src, items[i].bytes, cudaMemcpyHostToDevice, cx.stream));
+    *items[i].dst = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nn.SeqLSTM [upstream rnn], SURVEY.md Appendix C.  Forward: one batched x-projection (or per step in
+// the non-saving mode) + per step {recurrent GEMM, pointwise}.
+// ------------------------------------------------------------------------------------------------
+void Engine::lstm_forward(LstmRun& r, bool save) {
+  const Seg& ws = lay.segs[r.wseg];
+  VD_REQUIRE(ws.rows == r.D + r.H && ws.cols == 4 * r.H, VD_E_STATE, "lstm weight shape");
+  const int H = r.H, D = r.D, G = 4 * r.H;
+  const int64_t R = r.R;
+  const float* WtS = Wtp(r.wseg);          // [4H, D+H]
+  const float* bias = Wp(r.wseg + 1);
+  const float* A = r.x ? r.x : Wp(0);
+  const int64_t lda = r.x ? D : cfg.E;
+  r.saved = save;
+  if (save) {
+    r.h = arena.get<float>((int64_t)r.T * R * H);
+    r.c = arena.get<float>((int64_t)r.T * R * H);
+    r.gates = arena.get<float>((int64_t)r.T * R * G);
+    gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, nullptr, 0);
+  } else {
+    r.h = arena.get<float>(2 * R * H);
+    r.c = arena.get<float>(2 * R * H);
+    r.gates = arena.get<float>(R * G);
+  }
+  for (int t = 0; t < r.T; ++t) {
+    const int64_t slot = save ? t : (t & 1), pslot = save ? t - 1 : ((t - 1) & 1);
+    float* g = save ? r.gates + (int64_t)t * R * G : r.gates;
+    const float* hp = t > 0 ? r.h + pslot * R * H : r.h0;
+    const float* cp = t > 0 ? r.c + pslot * R * H : r.c0;
+    LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * (H + (save ? 0 : D)), 4.0 * R * (G + 4.0 * H));
+    if (!save) {
+      const float* At = r.x ? r.x + (int64_t)t * R * D : A;
+      gemm_tn((int)R, G, D, At, lda, r.gather ? r.gather + (int64_t)t * R : nullptr, WtS, D + H, g, G, 0.f, nullptr, 0);
+    }
+    if (hp) gemm_tn((int)R, G, H, hp, H, nullptr, WtS + D, D + H, g, G, 1.f, nullptr, 0);
+    lstm_pointwise_fwd(cx, g, bias, cp, r.mask ? r.mask + (int64_t)t * R : nullptr, r.c + slot * R * H,
+                       r.h + slot * R * H, R, H);
+  }
+}
+
+void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last, float* dx_out,
+                           float* dh0_out, float* dc0_out) {
+  VD_REQUIRE(r.saved, VD_E_STATE, "lstm_backward needs a forward run in training mode");
+  const int H = r.H, D = r.D, G = 4 * r.H;
+  const int64_t R = r.R, TR = (int64_t)r.T * R;
+  const float* Ws = Wp(r.wseg);            // (D+H, 4H)
+  float* da = arena.get<float>(TR * G);
+  float* dc_carry = arena.get<float>(R * H);
+  float* dh_rec = arena.get<float>(R * H);
+  VD_CUDA_CHECK(cudaMemsetAsync(dc_carry, 0, (size_t)R * H * sizeof(float), cx.stream));
+  for (int t = r.T - 1; t >= 0; --t) {
+    const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
+    const float* rec = (t == r.T - 1) ? dh_last : dh_rec;
+    const float* ext = dh_all ? dh_all + (int64_t)t * R * H : nullptr;
+    float* da_t = da + (int64_t)t * R * G;
+    LaunchCtx::Scope sc(&cx, "lstm_step_bwd", 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
+    lstm_pointwise_bwd(cx, r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, rec, ext,
+                       (t == r.T - 1) ? dc_last : nullptr, dc_carry, r.mask ? r.mask + (int64_t)t * R : nullptr, da_t, R, H);
+    float* dst = t > 0 ? dh_rec : dh0_out;
+    if (dst) gemm_tn((int)R, H, G, da_t, G, nullptr, Ws + (int64_t)D * G, G, dst, H, 0.f, nullptr, 0);
+  }
+  if (dc0_out) VD_CUDA_CHECK(cudaMemcpyAsync(dc0_out, dc_carry, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
+  // accGradParameters
+  float* dWs = dWp(r.wseg);
+  const float* A = r.x ? r.x : Wp(0);
+  const int64_t lda = r.x ? D : cfg.E;
+  gemm_atb(D, G, TR, A, lda, r.gather, da, G, dWs, G);
+  if (r.T > 1) gemm_atb(H, G, TR - R, r.h, H, nullptr, da + R * G, G, dWs + (int64_t)D * G, G);
+  if (r.h0) gemm_atb(H, G, R, r.h0, H, nullptr, da, G, dWs + (int64_t)D * G, G);
+  colsum_add(cx, dWp(r.wseg + 1), da, TR, G, G);
+  if (dx_out) gemm_tn((int)TR, D, G, da, G, nullptr, Ws, G, dx_out, D, 0.f, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoders
+// ------------------------------------------------------------------------------------------------
+static LstmRun make_run(int T, int64_t R, int D, int H, int wseg, const float* x, const int32_t* gather, const int32_t* mask) {
+  LstmRun r; r.T = T; r.R = R; r.D = D; r.H = H; r.wseg = wseg; r.x = x; r.gather = gather; r.mask = mask;
+  return r;
+}
+
+void Engine::encoder_forward(const vd_batch* b) {
+  VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  arena.reset();
+  have_fwd = false;
+  stage_batch(b);
+  save_acts = training != 0;
+  refresh_shadows();
+  conn_dh_l1 = conn_dc_l1 = conn_dc_l2 = nullptr;
+  gen_h0[0] = gen_h0[1] = gen_c0[0] = gen_c0[1] = nullptr;
+  const int E = cfg.E, H = cfg.H, R = cfg.R;
+  const int64_t N = db.N;
+  const int B = db.B;
+  const DropCfg d05 = dropcfg(0.5f), dp = dropcfg(cfg.dropout), dnone = dropcfg(0.f);
+  // time-major ids: the view(-1,T):t() of model.lua:255-257,274-278
+  ids_q = arena.get<int32_t>(N * db.Tq);
+  transpose_ids(cx, db.ques, ids_q, N, db.Tq);
+  if (cfg.useHist) {
+    ids_h = arena.get<int32_t>(N * db.Th);
+    transpose_ids(cx, db.hist, ids_h, N, db.Th);
+  }
+  const bool embdrop = cfg.enc == ENC_MN_ATT;              // mn-att-ques-im-hist.lua:24-25
+  // history branch
+  if (cfg.useHist) {
+    xh = arena.get<float>(N * db.Th * E);
+    embed_rows(cx, xh, Wp(0), ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
+    hist1 = make_run(db.Th, N, E, H, seg("hist.lstm1.weight"), xh, nullptr, ids_h);
+    hist2 = make_run(db.Th, N, H, H, seg("hist.lstm2.weight"), nullptr, nullptr, ids_h);
+  }
+  // The 2nd layer consumes every step of the 1st, so encoder LSTMs always keep all steps (T*N*H is small).
+  auto run_two = [&](LstmRun& l1, LstmRun& l2) {
+    lstm_forward(l1, true);
+    l2.x = l1.h;
+    lstm_forward(l2, true);
+  };
+  if (cfg.useHist) { run_two(hist1, hist2); }
+  // question branch
+  xq = arena.get<float>(N * db.Tq * E);
+  embed_rows(cx, xq, Wp(0), ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
+  if (cfg.enc == ENC_HREA) {
+    // hrea-ques-im-hist.lua:45-55: Dropout(0.5) -> Linear(F,IE) on the 10x repeated fc7, MaskTime, JoinTable(-1)
+    img_d = arena.get<float>(N * cfg.F);
+    repeat_rows(cx, img_d, db.img, B, R, cfg.F);
+    dropout_apply(cx, img_d, img_d, N * cfg.F, d05, SITE_IMG_FC7);
+    img_e = arena.get<float>(N * cfg.IE);
+    linear_fwd(seg("img.embed.weight"), img_d, N, img_e, 0);
+    qi_in = arena.get<float>(N * db.Tq * (E + cfg.IE));
+    masktime_concat_fwd(cx, qi_in, xq, img_e, ids_q, db.Tq, N, E, cfg.IE);
+    ques1 = make_run(db.Tq, N, E + cfg.IE, H, seg("ques.lstm1.weight"), qi_in, nullptr, ids_q);
+  } else {
+    ques1 = make_run(db.Tq, N, E, H, seg("ques.lstm1.weight"), xq, nullptr, ids_q);
+  }
+  ques2 = make_run(db.Tq, N, H, H, seg("ques.lstm2.weight"), nullptr, nullptr, ids_q);
+  run_two(ques1, ques2);
+  const float* q3 = ques2.h_last();
+  const float* h3 = cfg.useHist ? hist2.h_last() : nullptr;
+  encOut = arena.get<float>(N * H);
+
+  if (cfg.enc == ENC_LF_QUES || cfg.enc == ENC_LF_QIH) {
+    // lf-ques.lua:29-33 / lf-ques-im-hist.lua:49-59
+    joinK = cfg.enc == ENC_LF_QUES ? H : 2 * H + cfg.F;
+    join_d = arena.get<float>(N * joinK);
+    copy_cols(cx, join_d, joinK, q3, H, N, H);
+    if (cfg.enc == ENC_LF_QIH) {
+      // image repeated per round (model.lua:267-269), concat order [q | img | h]
+      float* tmp = arena.get<float>(N * cfg.F);
+      repeat_rows(cx, tmp, db.img, B, R, cfg.F);
+      copy_cols(cx, join_d + H, joinK, tmp, cfg.F, N, cfg.F);
+      copy_cols(cx, join_d + H + cfg.F, joinK, h3, H, N, H);
+    }
+    dropout_apply(cx, join_d, join_d, N * joinK, dp, SITE_FUSION);
+    linear_fwd(seg("fusion.weight"), join_d, N, encOut, 1);
+  } else if (cfg.enc == ENC_HREA) {
+    // hrea-ques-im-hist.lua:89-137
+    sq = arena.get<float>(N); sh = arena.get<float>(N);
+    int sq_w = seg("att.q.weight"), sh_w = seg("att.h.weight");
+    rowdot_fwd(cx, sq, q3, Wp(sq_w), Wp(sq_w + 1), N, H);
+    rowdot_fwd(cx, sh, h3, Wp(sh_w), Wp(sh_w + 1), N, H);
+    probs = arena.get<float>((int64_t)B * R * R);
+    att = arena.get<float>(N * H);
+    hrea_attention_fwd(cx, sq, sh, h3, probs, att, B, R, H);
+    // JoinTable(-1) [att | Qi], View(-1,10,2H), Transpose(1,2): row (r,b) <- row (b,r)
+    jt = arena.get<float>(N * 2 * H);
+    float* j = arena.get<float>(N * 2 * H);
+    copy_cols(cx, j, 2 * H, att, H, N, H);
+    copy_cols(cx, j + H, 2 * H, q3, H, N, H);
+    // permute rows (b,r) -> (r,b) with a strided 2-D copy per round
+    for (int rr = 0; rr < R; ++rr)
+      copy_cols(cx, jt + (int64_t)rr * B * 2 * H, 2 * H, j + (int64_t)rr * 2 * H, (int64_t)R * 2 * H, B, 2 * H);
+    dialog = make_run(R, B, 2 * H, H, seg("dialog.lstm.weight"), jt, nullptr, nullptr);
+    lstm_forward(dialog, true);
+    for (int rr = 0; rr < R; ++rr)
+      copy_cols(cx, encOut + (int64_t)rr * H, (int64_t)R * H, dialog.h + (int64_t)rr * B * H, H, B, H);
+  } else {
+    // mn-att-ques-im-hist.lua:48-106
+    const int P = cfg.S * cfg.S, Cm = cfg.Cm;
+    probs = arena.get<float>((int64_t)B * R * R);
+    hAtt = arena.get<float>(N * H);
+    mn_attention_fwd(cx, q3, h3, probs, hAtt, B, R, H);
+    hAtt_d = arena.get<float>(N * H);
+    dropout_apply(cx, hAtt_d, hAtt, N * H, d05, SITE_HATT);
+    hAttTr = arena.get<float>(N * H);
+    linear_fwd(seg("mn.fact.weight"), hAtt_d, N, hAttTr, 1);
+    sum1 = arena.get<float>(N * H);
+    add_out(cx, sum1, hAttTr, q3, N * H);
+    qh2 = arena.get<float>(N * H);
+    linear_fwd(seg("mn.query.weight"), sum1, N, qh2, 1);
+    // SAN: tanh(Linear(img)) is computed once per dialog; Dropout then acts on the repeated tensor (:74-78)
+    t_img = arena.get<float>((int64_t)B * P * H);
+    linear_fwd(seg("san.img.weight"), db.img, (int64_t)B * P, t_img, 1);
+    img_tr = arena.get<float>(N * P * H);
+    san_expand_dropout(cx, img_tr, t_img, B, R, P, H, d05, SITE_IMG_TR);
+    img_common.assign(cfg.hops, nullptr); ques_common.assign(cfg.hops, nullptr);
+    sc.assign(cfg.hops, nullptr); pr.assign(cfg.hops, nullptr); u_hop.assign(cfg.hops + 1, nullptr);
+    u_hop[0] = qh2;
+    for (int hop = 0; hop < cfg.hops; ++hop) {
+      std::string pre = "san.hop" + std::to_string(hop + 1) + ".";
+      int w_ic = seg((pre + "img_common.weight").c_str()), w_qc = seg((pre + "ques_common.weight").c_str()),
+          w_s = seg((pre + "score.weight").c_str());
+      img_common[hop] = arena.get<float>(N * P * Cm);
+      linear_fwd(w_ic, img_tr, N * P, img_common[hop], 0);
+      ques_common[hop] = arena.get<float>(N * Cm);
+      linear_fwd(w_qc, u_hop[hop], N, ques_common[hop], 0);
+      sc[hop] = arena.get<float>(N * P);
+      san_score_fwd(cx, img_common[hop], ques_common[hop], Wp(w_s), Wp(w_s + 1), sc[hop], N, P, Cm, d05, SITE_HOP0 + hop);
+      pr[hop] = arena.get<float>(N * P);
+      u_hop[hop + 1] = arena.get<float>(N * H);
+      san_softmax_att_fwd(cx, sc[hop], pr[hop], img_tr, u_hop[hop], u_hop[hop + 1], N, P, H);
+    }
+    u_d = arena.get<float>(N * H);
+    dropout_apply(cx, u_d, u_hop[cfg.hops], N * H, d05, SITE_U_OUT);
+    linear_fwd(seg("san.out.weight"), u_d, N, encOut, 1);
+  }
+  have_fwd = true;
+}
+
+void Engine::encoder_backward(const float* dEnc) {
+  VD_REQUIRE(have_fwd && save_acts, VD_E_STATE, "encoder_backward: no training-mode forward to back-propagate");
+  VD_REQUIRE(dEnc != nullptr, VD_E_BADARG, "gradEncOut is null");
+  const int E = cfg.E, H = cfg.H, R = cfg.R;
+  const int64_t N = db.N;
+  const int B = db.B;
+  const DropCfg d05 = dropcfg(0.5f), dp = dropcfg(cfg.dropout), dnone = dropcfg(0.f);
+  float* dq3 = arena.get<float>(N * H);
+  float* dh3 = cfg.useHist ? arena.get<float>(N * H) : nullptr;
+  float* dpre = arena.get<float>(N * H);
+
+  if (cfg.enc == ENC_LF_QUES || cfg.enc == ENC_LF_QIH) {
+    tanh_bwd(cx, dpre, dEnc, encOut, N * H);
+    float* dj = arena.get<float>(N * joinK);
+    linear_bwd(seg("fusion.weight"), join_d, dpre, N, dj, 0.f);
+    dropout_apply(cx, dj, dj, N * joinK, dp, SITE_FUSION);
+    copy_cols(cx, dq3, H, dj, joinK, N, H);
+    if (cfg.enc == ENC_LF_QIH) copy_cols(cx, dh3, H, dj + H + cfg.F, joinK, N, H);
+  } else if (cfg.enc == ENC_HREA) {
+    const float* q3 = ques2.h_last();
+    const float* h3 = hist2.h_last();
+    // un-permute the gradient (n = b*R + r) -> (r,b), BPTT over rounds
+    float* dd = arena.get<float>(N * H);
+    for (int rr = 0; rr < R; ++rr)
+      copy_cols(cx, dd + (int64_t)rr * B * H, H, dEnc + (int64_t)rr * H, (int64_t)R * H, B, H);
+    float* djt = arena.get<float>(N * 2 * H);
+    lstm_backward(dialog, dd, nullptr, nullptr, djt, nullptr, nullptr);
+    float* dj = arena.get<float>(N * 2 * H);
+    for (int rr = 0; rr < R; ++rr)
+      copy_cols(cx, dj + (int64_t)rr * 2 * H, (int64_t)R * 2 * H, djt + (int64_t)rr * B * 2 * H, 2 * H, B, 2 * H);
+    float* datt = arena.get<float>(N * H);
+    copy_cols(cx, datt, H, dj, 2 * H, N, H);
+    copy_cols(cx, dq3, H, dj + H, 2 * H, N, H);
+    float* dsq = arena.get<float>(N); float* dsh = arena.get<float>(N);
+    hrea_attention_bwd(cx, sq, sh, h3, probs, datt, dsq, dsh, dh3, B, R, H);
+    int sq_w = seg("att.q.weight"), sh_w = seg("att.h.weight");
+    rowdot_bwd(cx, dsq, q3, Wp(sq_w), dq3, 1, dWp(sq_w), dWp(sq_w + 1), N, H);
+    rowdot_bwd(cx, dsh, h3, Wp(sh_w), dh3, 1, dWp(sh_w), dWp(sh_w + 1), N, H);
+  } else {
+    const int P = cfg.S * cfg.S, Cm = cfg.Cm;
+    const float* q3 = ques2.h_last();
+    const float* h3 = hist2.h_last();
+    tanh_bwd(cx, dpre, dEnc, encOut, N * H);
+    float* du = arena.get<float>(N * H);
+    linear_bwd(seg("san.out.weight"), u_d, dpre, N, du, 0.f);
+    dropout_apply(cx, du, du, N * H, d05, SITE_U_OUT);
+    float* dimg_tr = arena.get<float>(N * P * H);
+    float* ds = arena.get<float>(N * P);
+    float* dic = arena.get<float>(N * P * Cm);
+    float* dqc = arena.get<float>(N * Cm);
+    for (int hop = cfg.hops - 1; hop >= 0; --hop) {
+      std::string pre = "san.hop" + std::to_string(hop + 1) + ".";
+      int w_ic = seg((pre + "img_common.weight").c_str()), w_qc = seg((pre + "ques_common.weight").c_str()),
+          w_s = seg((pre + "score.weight").c_str());
+      if (hop == cfg.hops - 1) {
+        san_att_bwd(cx, du, pr[hop], img_tr, ds, dimg_tr, N, P, H);
+      } else {
+        float* tmp = arena.get<float>(N * P * H);
+        san_att_bwd(cx, du, pr[hop], img_tr, ds, tmp, N, P, H);
+        add_inplace(cx, dimg_tr, tmp, N * P * H);
+      }
+      san_score_bwd(cx, ds, img_common[hop], ques_common[hop], Wp(w_s), dic, dqc, dWp(w_s), dWp(w_s + 1), N, P, Cm, d05,
+                    SITE_HOP0 + hop);
+      linear_bwd(w_ic, img_tr, dic, N * P, dimg_tr, 1.f);
+      linear_bwd(w_qc, u_hop[hop], dqc, N, du, 1.f);          // du now = grad wrt u_hop[hop]
+    }
+    float* dt_pre = arena.get<float>((int64_t)B * P * H);
+    san_collapse_bwd(cx, dimg_tr, t_img, dt_pre, B, R, P, H, d05, SITE_IMG_TR);
+    linear_bwd(seg("san.img.weight"), db.img, dt_pre, (int64_t)B * P, nullptr, 0.f);
+    // memory network part, :48-65
+    tanh_bwd(cx, dpre, du, qh2, N * H);
+    float* dsum1 = arena.get<float>(N * H);
+    linear_bwd(seg("mn.query.weight"), sum1, dpre, N, dsum1, 0.f);
+    tanh_bwd(cx, dpre, dsum1, hAttTr, N * H);
+    float* dhAtt = arena.get<float>(N * H);
+    linear_bwd(seg("mn.fact.weight"), hAtt_d, dpre, N, dhAtt, 0.f);
+    dropout_apply(cx, dhAtt, dhAtt, N * H, d05, SITE_HATT);
+    mn_attention_bwd(cx, q3, h3, probs, dhAtt, dq3, dh3, B, R, H);
+    add_inplace(cx, dq3, dsum1, N * H);
+  }
+
+  // question LSTMs (+ gradients handed back by the gen decoder, gen.lua:45-60)
+  const bool embdrop = cfg.enc == ENC_MN_ATT;
+  {
+    float* dx2 = arena.get<float>(N * db.Tq * H);
+    lstm_backward(ques2, nullptr, dq3, conn_dc_l2, dx2, nullptr, nullptr);
+    int D1 = ques1.D;
+    float* dx1 = arena.get<float>(N * db.Tq * D1);
+    lstm_backward(ques1, dx2, conn_dh_l1, conn_dc_l1, dx1, nullptr, nullptr);
+    embed_scatter_add(cx, dWp(0), dx1, D1, ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
+    if (cfg.enc == ENC_HREA) {
+      float* die = arena.get<float>(N * cfg.IE);
+      masktime_bwd(cx, dx1, D1, E, ids_q, die, db.Tq, N, cfg.IE);
+      linear_bwd(seg("img.embed.weight"), img_d, die, N, nullptr, 0.f);
+    }
+  }
+  if (cfg.useHist) {
+    float* dx2 = arena.get<float>(N * db.Th * H);
+    lstm_backward(hist2, nullptr, dh3, nullptr, dx2, nullptr, nullptr);
+    float* dx1 = arena.get<float>(N * db.Th * E);
+    lstm_backward(hist1, dx2, nullptr, nullptr, dx1, nullptr, nullptr);
+    embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoders + criterions
+// ------------------------------------------------------------------------------------------------
+void Engine::forward_connect() {
+  // decoders/gen.lua:30-42; decoders/disc.lua:35 is a no-op
+  if (cfg.dec != DEC_GEN) return;
+  VD_REQUIRE(have_fwd, VD_E_STATE, "forward_connect before encoder_forward");
+  gen_h0[0] = gen_h0[1] = gen_c0[0] = gen_c0[1] = nullptr;
+  if (cfg.enc != ENC_MN_ATT) {                       // encoders with .rnnLayers
+    gen_h0[0] = ques1.h_last(); gen_c0[0] = ques1.c_last();
+    gen_c0[1] = ques2.c_last();
+  }
+  gen_h0[1] = encOut;
+}
+
+void Engine::decoder_forward() {
+  VD_REQUIRE(have_fwd, VD_E_STATE, "decoder_forward before encoder_forward");
+  const int E = cfg.E, H = cfg.H, K = cfg.K;
+  const int64_t N = db.N;
+  if (cfg.dec == DEC_DISC) {
+    VD_REQUIRE(db.options && db.To > 0, VD_E_SHAPE, "disc decoder: options / To missing");
+    const int64_t Ro = N * K;
+    ids_o = arena.get<int32_t>(Ro * db.To);
+    transpose_ids(cx, db.options, ids_o, Ro, db.To);
+    opt = make_run(db.To, Ro, E, H, seg("opt.lstm.weight"), nullptr, ids_o, nullptr);   // disc.lua:4-5: no maskzero
+    lstm_forward(opt, save_acts);
+    scores = arena.get<float>(N * K);
+    disc_scores_fwd(cx, opt.h_last(), encOut, scores, N, K, H);
+  } else {
+    VD_REQUIRE(db.answer_in && db.Ta > 0, VD_E_SHAPE, "gen decoder: answer_in / Ta missing");
+    forward_connect();
+    ids_ai = arena.get<int32_t>(N * db.Ta);
+    transpose_ids(cx, db.answer_in, ids_ai, N, db.Ta);
+    float* xa = arena.get<float>(N * db.Ta * E);
+    embed_rows(cx, xa, Wp(0), ids_ai, N * db.Ta, E, dropcfg(0.f), 0);
+    dec1 = make_run(db.Ta, N, E, H, seg("dec.lstm1.weight"), xa, nullptr, ids_ai);
+    dec1.h0 = gen_h0[0]; dec1.c0 = gen_c0[0];
+    lstm_forward(dec1, true);
+    dec2 = make_run(db.Ta, N, H, H, seg("dec.lstm2.weight"), dec1.h, nullptr, ids_ai);
+    dec2.h0 = gen_h0[1]; dec2.c0 = gen_c0[1];
+    lstm_forward(dec2, true);
+    logp = arena.get<float>(N * db.Ta * cfg.V);
+    linear_fwd(seg("dec.out.weight"), dec2.h, N * db.Ta, logp, 0);
+    logsoftmax_rows(cx, logp, ids_ai, N * db.Ta, cfg.V);            // gen.lua:23-24 (MaskZero)
+  }
+}
+
+float Engine::criterion_forward() {
+  const int64_t N = db.N;
+  if (cfg.dec == DEC_DISC) {
+    VD_REQUIRE(scores && db.answer_ind, VD_E_STATE, "criterion: decoder_forward / answer_ind missing");
+    row_loss = arena.get<float>(N);
+    xent_fwd(cx, scores, db.answer_ind, row_loss, N, cfg.K);
+    reduce_sum(cx, row_loss, scalars_dev, N, 1.f / (float)N);        // CrossEntropyCriterion: mean
+  } else {
+    VD_REQUIRE(logp && db.answer_out, VD_E_STATE, "criterion: decoder_forward / answer_out missing");
+    ids_ao = arena.get<int32_t>(N * db.Ta);
+    transpose_ids(cx, db.answer_out, ids_ao, N, db.Ta);
+    row_loss = arena.get<float>(N * db.Ta);
+    nll_fwd(cx, logp, ids_ao, ids_ai, row_loss, N * db.Ta, cfg.V);
+    reduce_sum(cx, row_loss, scalars_dev, N * db.Ta, 1.f);            // ClassNLL sizeAverage=false
+  }
+  float loss = 0.f;
+  VD_CUDA_CHECK(cudaMemcpyAsync(&loss, scalars_dev, sizeof(float), cudaMemcpyDeviceToHost, cx.stream));
+  VD_CUDA_CHECK(cudaStreamSynchronize(cx.stream));                    // the reference reads curLoss here too (model.lua:330)
+  return loss;
+}
+
+void Engine::criterion_backward() {
+  const int64_t N = db.N;
+  if (cfg.dec == DEC_DISC) {
+    VD_REQUIRE(scores && db.answer_ind, VD_E_STATE, "criterion_backward: decoder_forward / answer_ind missing");
+    dscores = arena.get<float>(N * cfg.K);
+    xent_bwd(cx, scores, db.answer_ind, dscores, N, cfg.K);
+  } else {
+    VD_REQUIRE(logp && ids_ao, VD_E_STATE, "criterion_backward before criterion_forward");
+    dlogits = arena.get<float>(N * db.Ta * cfg.V);
+    nll_bwd(cx, logp, ids_ao, ids_ai, dlogits, N * db.Ta, cfg.V);
+  }
+}
+
+void Engine::decoder_backward() {
+  VD_REQUIRE(save_acts, VD_E_STATE, "decoder_backward needs a training-mode forward");
+  const int E = cfg.E, H = cfg.H, K = cfg.K;
+  const int64_t N = db.N;
+  dEncFromDec = arena.get<float>(N * H);
+  if (cfg.dec == DEC_DISC) {
+    VD_REQUIRE(dscores, VD_E_STATE, "decoder_backward before criterion_backward");
+    const int64_t Ro = N * K;
+    float* dfeat = arena.get<float>(Ro * H);
+    disc_scores_bwd(cx, dscores, opt.h_last(), encOut, dfeat, dEncFromDec, N, K, H);
+    float* dx = arena.get<float>(Ro * db.To * E);
+    lstm_backward(opt, nullptr, dfeat, nullptr, dx, nullptr, nullptr);
+    embed_scatter_add(cx, dWp(0), dx, E, ids_o, Ro * db.To, E, dropcfg(0.f), 0);
+  } else {
+    VD_REQUIRE(dlogits, VD_E_STATE, "decoder_backward before criterion_backward");
+    float* do2 = arena.get<float>(N * db.Ta * H);
+    linear_bwd(seg("dec.out.weight"), dec2.h, dlogits, N * db.Ta, do2, 0.f);
+    for (int l = 0; l < 2; ++l) { gen_dh0[l] = arena.get<float>(N * H); gen_dc0[l] = arena.get<float>(N * H); }
+    float* dx2 = arena.get<float>(N * db.Ta * H);
+    lstm_backward(dec2, do2, nullptr, nullptr, dx2, gen_dh0[1], gen_dc0[1]);
+    float* dx1 = arena.get<float>(N * db.Ta * E);
+    lstm_backward(dec1, dx2, nullptr, nullptr, dx1, gen_dh0[0], gen_dc0[0]);
+    embed_scatter_add(cx, dWp(0), dx1, E, ids_ai, N * db.Ta, E, dropcfg(0.f), 0);
+  }
+}
+
+const float* Engine::backward_connect() {
+  // decoders/gen.lua:45-60
+  if (cfg.dec == DEC_DISC) return dEncFromDec;     // t[2] of model.lua:335
+  conn_dh_l1 = conn_dc_l1 = conn_dc_l2 = nullptr;
+  if (cfg.enc != ENC_MN_ATT) {
+    conn_dc_l1 = gen_dc0[0]; conn_dc_l2 = gen_dc0[1];
+    conn_dh_l1 = gen_dh0[0];
+  }
+  return gen_dh0[1];
+}
+
+// Model:retrieveBatch (model.lua:344-430)
+void Engine::retrieve(const vd_batch* b, int use_gt, int32_t* ranks_host) {
+  VD_REQUIRE(ranks_host != nullptr, VD_E_BADARG, "ranks_host is null");
+  int saved_training = training;
+  training = 0;
+  try {
+    encoder_forward(b);
+    const int64_t N = db.N;
+    const float* sc_dev = nullptr;
+    if (cfg.dec == DEC_DISC) { decoder_forward(); sc_dev = scores; }
+    else { gen_option_lhood(); sc_dev = lhood; }
+    if (use_gt) VD_REQUIRE(db.answer_ind, VD_E_SHAPE, "use_gt needs answer_ind");
+    int64_t nout = use_gt ? N : N * cfg.K;
+    int32_t* ranks = arena.get<int32_t>(nout);
+    rank_rows(cx, sc_dev, use_gt ? db.answer_ind : nullptr, ranks, N, cfg.K);
+    VD_CUDA_CHECK(cudaMemcpyAsync(ranks_host, ranks, (size_t)nout * sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    VD_CUDA_CHECK(cudaStreamSynchronize(cx.stream));
+  } catch (...) { training = saved_training; throw; }
+  training = saved_training;
+}
+
+// gen retrieval: the 100-iteration option loop of model.lua:405-415 batched over (N*100) rows, log-likelihood
+// accumulated per time step without materialising (T,N*100,V) log-probs.
+void Engine::gen_option_lhood() {
+  VD_REQUIRE(cfg.dec == DEC_GEN, VD_E_STATE, "gen_option_lhood needs the gen decoder");
+  VD_REQUIRE(have_fwd && db.option_in && db.option_out && db.To > 0, VD_E_SHAPE, "option_in / option_out / To missing");
+  const int E = cfg.E, H = cfg.H, K = cfg.K, V = cfg.V;
+  const int64_t N = db.N, Ro = N * K;
+  forward_connect();
+  int32_t* oi = arena.get<int32_t>(Ro * db.To);
+  int32_t* oo = arena.get<int32_t>(Ro * db.To);
+  transpose_ids(cx, db.option_in, oi, Ro, db.To);
+  transpose_ids(cx, db.option_out, oo, Ro, db.To);
+  // (h0,c0) repeated over the K options of a round: row (n,k) <- row n
+  const float* h0[2] = {nullptr, nullptr}; const float* c0[2] = {nullptr, nullptr};
+  for (int l = 0; l < 2; ++l) {
+    if (gen_h0[l]) { float* t = arena.get<float>(Ro * H); repeat_rows(cx, t, gen_h0[l], N, K, H); h0[l] = t; }
+    if (gen_c0[l]) { float* t = arena.get<float>(Ro * H); repeat_rows(cx, t, gen_c0[l], N, K, H); c0[l] = t; }
+  }
+  LstmRun l1 = make_run(db.To, Ro, E, H, seg("dec.lstm1.weight"), nullptr, oi, oi);
+  l1.h0 = h0[0]; l1.c0 = c0[0];
+  lstm_forward(l1, true);
+  LstmRun l2 = make_run(db.To, Ro, H, H, seg("dec.lstm2.weight"), l1.h, nullptr, oi);
+  l2.h0 = h0[1]; l2.c0 = c0[1];
+  lstm_forward(l2, true);
+  lhood = arena.get<float>(Ro);
+  VD_CUDA_CHECK(cudaMemsetAsync(lhood, 0, (size_t)Ro * sizeof(float), cx.stream));
+  float* logits = arena.get<float>(Ro * V);
+  int wo = seg("dec.out.weight");
+  for (int t = 0; t < db.To; ++t) {
+    linear_fwd(wo, l2.h + (int64_t)t * Ro * H, Ro, logits, 0);
+    lhood_accumulate(cx, logits, oo + (int64_t)t * Ro, oi + (int64_t)t * Ro, lhood, Ro, V);
+  }
+}
+
+// model.lua:96-99 + optim_updates.lua:62-91
+void Engine::clamp_adam_step(float lr) {
+  VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  float gscale = 1.f;
+  if (world > 1) {
+    allreduce_grads();
+    // disc: loss is a mean over the local N rows -> average over ranks; gen: a sum -> plain sum
+    if (cfg.dec == DEC_DISC) gscale = 1.f / (float)world;
+  }
+  adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  double bc1 = 1.0 - pow(b1, (double)adam_t), bc2 = 1.0 - pow(b2, (double)adam_t);
+  float step = (float)((double)lr * sqrt(bc2) / bc1);
+  clamp_adam(cx, W, dW, m, v, nparams, step, (float)b1, (float)b2, 1e-8f, gscale);
+}
+
+}  // namespace vd

@@ -1,0 +1,158 @@
+// Engine: owns parameters, activations and the per-batch forward/backward orchestration that
+// replaces Model:forwardBackward / Model:retrieveBatch (/root/reference/model.lua:249-430).
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/visdial_b200.h"
+#include "kernels.cuh"
+
+namespace vd {
+
+enum EncKind { ENC_LF_QUES = 0, ENC_LF_QIH = 1, ENC_HREA = 2, ENC_MN_ATT = 3 };
+enum DecKind { DEC_DISC = 0, DEC_GEN = 1 };
+
+struct Cfg {
+  std::string encoder, decoder;
+  int enc = 0, dec = 0;
+  int V = 0, E = 300, H = 512, L = 2, F = 4096, S = 14, IE = 300, Cm = 512, hops = 1, R = 10, K = 100;
+  float dropout = 0.5f;
+  int gpuid = 0;
+  bool useIm = false, useHist = false, att = false;
+};
+Cfg parse_cfg(const vd_params* p);
+
+struct Seg {
+  std::string name;
+  int64_t off = 0, rows = 0, cols = 0;
+  int init = 0;
+  int64_t fan_in = 0;
+};
+struct Layout {
+  std::vector<Seg> segs;
+  int64_t total = 0;
+  int find(const std::string& name) const;
+};
+Layout build_layout(const Cfg& c);
+
+// grow-only bump allocator for activations (reset at every new forward)
+struct Arena {
+  struct Chunk { char* p; size_t cap; size_t used; };
+  std::vector<Chunk> chunks;
+  size_t cur = 0;
+  void* alloc(size_t bytes);
+  template <typename T> T* get(int64_t n) { return reinterpret_cast<T*>(alloc((size_t)n * sizeof(T))); }
+  void reset();
+  void release();
+};
+
+// one nn.SeqLSTM execution (forward state kept for BPTT)
+struct LstmRun {
+  int T = 0; int64_t R = 0; int D = 0, H = 0;
+  int wseg = -1;
+  const float* x = nullptr;          // dense (T*R, D) or null when rows are gathered from the embedding
+  const int32_t* gather = nullptr;   // time-major ids (T*R) for the gather
+  const int32_t* mask = nullptr;     // time-major ids (T*R) for maskzero
+  const float* h0 = nullptr; const float* c0 = nullptr;
+  float* h = nullptr; float* c = nullptr; float* gates = nullptr;
+  bool saved = false;
+  const float* h_last() const { return h + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
+  const float* c_last() const { return c + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
+};
+
+struct DevBatch {
+  int B = 0, Tq = 0, Th = 0, Ta = 0, To = 0; int64_t N = 0;
+  const int32_t* ques = nullptr; const int32_t* hist = nullptr; const float* img = nullptr;
+  const int32_t* options = nullptr; const int32_t* answer_ind = nullptr;
+  const int32_t* answer_in = nullptr; const int32_t* answer_out = nullptr;
+  const int32_t* option_in = nullptr; const int32_t* option_out = nullptr;
+};
+
+struct GrowBuf {
+  void* p = nullptr; size_t cap = 0;
+  void* ensure(size_t bytes);
+  void release();
+};
+
+struct Engine {
+  Cfg cfg;
+  Layout lay;
+  LaunchCtx cx;
+  int64_t nparams = 0;
+  float *W = nullptr, *dW = nullptr, *m = nullptr, *v = nullptr, *Wt = nullptr;
+  int64_t adam_t = 0;
+  int64_t* segtab_dev = nullptr; int nseg2d = 0; int64_t max2d = 0;
+  int training = 1;
+  uint64_t drop_seed = 1234, drop_iter = 0;
+  int math_mode = VD_MATH_TF32;
+  Arena arena;
+  GrowBuf stage[9];
+  DevBatch db;
+  float* scalars_dev = nullptr;      // [0] loss
+  float* flush_buf = nullptr; int64_t flush_n = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+  // communicator (NCCL, loaded with dlopen)
+  void* nccl_comm = nullptr; int rank = 0, world = 1;
+
+  // ---- forward state ----
+  bool have_fwd = false, save_acts = false;
+  int32_t *ids_q = nullptr, *ids_h = nullptr, *ids_o = nullptr, *ids_ai = nullptr, *ids_ao = nullptr;
+  float *xq = nullptr, *xh = nullptr;
+  LstmRun ques1, ques2, hist1, hist2, dialog, opt, dec1, dec2;
+  float *encOut = nullptr;
+  // lf
+  float *join_d = nullptr; int joinK = 0;
+  // hrea
+  float *img_d = nullptr, *img_e = nullptr, *qi_in = nullptr, *sq = nullptr, *sh = nullptr, *probs = nullptr,
+        *att = nullptr, *jt = nullptr, *dial_out = nullptr;
+  // mn-att
+  float *hAtt = nullptr, *hAtt_d = nullptr, *hAttTr = nullptr, *sum1 = nullptr, *qh2 = nullptr, *t_img = nullptr,
+        *img_tr = nullptr, *u_d = nullptr;
+  std::vector<float*> img_common, ques_common, sc, pr, u_hop;   // per hop; u_hop[0] = qh2
+  // decoder
+  float *scores = nullptr, *dscores = nullptr, *row_loss = nullptr, *logp = nullptr, *dlogits = nullptr,
+        *lhood = nullptr;
+  const float *gen_h0[2] = {nullptr, nullptr}, *gen_c0[2] = {nullptr, nullptr};
+  float *gen_dh0[2] = {nullptr, nullptr}, *gen_dc0[2] = {nullptr, nullptr};
+  float *dEncFromDec = nullptr;
+  // connect grads handed to the encoder LSTMs (gen.lua:45-60)
+  const float *conn_dh_l1 = nullptr, *conn_dc_l1 = nullptr, *conn_dc_l2 = nullptr;
+
+  explicit Engine(const vd_params* p);
+  ~Engine();
+
+  // helpers
+  const float* Wp(int seg) const { return W + lay.segs[seg].off; }
+  const float* Wtp(int seg) const { return Wt + lay.segs[seg].off; }
+  float* dWp(int seg) const { return dW + lay.segs[seg].off; }
+  int seg(const char* name) const;
+  DropCfg dropcfg(float p) const;
+  void gemm_tn(int M, int N, int K, const float* A, int64_t lda, const int32_t* gather, const float* B, int64_t ldb,
+               float* C, int64_t ldc, float beta, const float* bias, int act);
+  void gemm_atb(int M, int N, int64_t K, const float* A, int64_t lda, const int32_t* gather, const float* B, int64_t ldb,
+                float* C, int64_t ldc);
+  // y = act(x W^T + b) with W = segment `wseg` (out,in), bias = wseg+1
+  void linear_fwd(int wseg, const float* x, int64_t rows, float* y, int act);
+  // dW += dy^T x ; db += colsum(dy) ; dx (=|+=) dy W
+  void linear_bwd(int wseg, const float* x, const float* dy, int64_t rows, float* dx, float beta_dx);
+  void refresh_shadows();
+  void stage_batch(const vd_batch* b);
+  void lstm_forward(LstmRun& r, bool save);
+  void lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last, float* dx_out,
+                     float* dh0_out, float* dc0_out);
+
+  void encoder_forward(const vd_batch* b);
+  void encoder_backward(const float* dEnc);
+  void forward_connect();
+  void decoder_forward();
+  float criterion_forward();
+  void criterion_backward();
+  void decoder_backward();
+  const float* backward_connect();
+  void retrieve(const vd_batch* b, int use_gt, int32_t* ranks_host);
+  void gen_option_lhood();
+  void clamp_adam_step(float lr);
+  void allreduce_grads();
+};
+
+}  // namespace vd

@@ -1,0 +1,116 @@
+"""Mirror of the reference's `Model` class (/root/reference/model.lua:8-430) over the C engine.
+Same method names, argument meaning and call order as the Lua original, so that the parity tests
+read like the reference's own driver code.  Beam search / sampling (model.lua:432-613) is out of
+scope."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import decoders, encoders
+from .engine import Batch, DEFAULT_PARAMS, derive_flags
+from .modules import Criterion, Sequential
+
+
+class Model:
+    def __init__(self, params: dict, seed: int = 1234):                  # model.lua:11-62
+        p = dict(DEFAULT_PARAMS)
+        p.update(params)
+        self.params = derive_flags(p)
+        encoder = encoders.load(p["encoder"])                             # :19-20
+        decoder = decoders.load(p["decoder"])                             # :22-23
+        enc = encoder.model(p)                                            # :25
+        dec = decoder.model(p, enc)                                       # :26
+        self.forwardConnect = decoder.forwardConnect                      # :28-29
+        self.backwardConnect = decoder.backwardConnect
+        self.decoderConnect = getattr(decoder, "decoderConnect", None)
+        self.criterion = Criterion(p["decoder"])                          # :32-39
+        self.wrapper = Sequential(enc, dec, p, seed)                      # :42 (weight-init.lua is a no-op here)
+        if p["gpuid"] < 0:
+            raise ValueError("visdial_b200 has no CPU path: gpuid must be >= 0")
+        self.wrapper.cuda()                                               # :48-51
+        self.criterion.engine = self.wrapper.engine
+        self.encoder = self.wrapper.get(1)                                # :53-54
+        self.decoder = self.wrapper.get(2)
+        self.wrapperW, self.wrapperdW = self.wrapper.getParameters()      # :55
+        self.wrapper.training()                                           # :57
+        self.optims = {"learningRate": p["learningRate"]}                 # :60-61
+        self.runningLoss = 0.0                                            # global `runningLoss`, train.lua:89
+        self.engine = self.wrapper.engine
+        self.iteration = 0
+
+    # ---------------------------------------------------------------------------------------------
+    def trainIteration(self, dataloader):                                 # model.lua:66-106
+        self.wrapper.zeroGradParameters()                                 # :68
+        batch = dataloader.getTrainBatch(self.params)                     # :71
+        if not isinstance(batch, Batch):
+            batch = Batch(batch)
+        self.iteration += 1
+        self.engine.set_dropout_seed(self.params.get("seed", 1234), self.iteration)
+        curLoss = self.forwardBackward(batch)                             # :74
+        if self.params["decoder"] == "gen":                               # :76-85
+            numTokens = int((batch["answer_out"] > 0).sum())
+            cur = curLoss / max(numTokens, 1)
+        else:                                                             # :86-93
+            cur = curLoss
+        self.runningLoss = 0.95 * self.runningLoss + 0.05 * cur if self.runningLoss > 0 else cur
+        # :96-99 clamp(-5,5) + adam, fused with the gradient all-reduce when world > 1
+        self.engine.clamp_adam_step(self.optims["learningRate"])
+        if self.optims["learningRate"] > self.params["minLRate"]:          # :102-105
+            self.optims["learningRate"] *= self.params["lrDecayRate"]
+        return curLoss
+
+    def forwardBackward(self, batch, onlyForward=False, encOutOnly=False):   # model.lua:249-342
+        if not isinstance(batch, Batch):
+            batch = Batch(batch)
+        # :252-294 (time-major views, image repeat, MN mask) are index arithmetic inside the engine
+        encOut = self.encoder.forward(batch)                               # :297
+        seqLen = batch.c.Tq
+        self.decoder._last_batch = batch
+        self.forwardConnect(self.encoder, self.decoder, encOut, seqLen)    # :300
+        if encOutOnly:
+            return encOut                                                  # :302
+        if self.params["decoder"] == "gen":
+            decOut = self.decoder.forward(batch)                           # :313
+            curLoss = self.criterion.forward(decOut, batch)                # :314
+            if not onlyForward:
+                gradCriterionOut = self.criterion.backward(decOut, batch)  # :318
+                self.decoder.backward(batch, gradCriterionOut)             # :319
+                gradDecOut = self.backwardConnect(self.encoder, self.decoder)   # :322
+                self.encoder.backward(batch, gradDecOut)                   # :323
+        else:
+            decOut = self.decoder.forward(batch)                           # :329
+            curLoss = self.criterion.forward(decOut, batch)                # :330
+            if not onlyForward:
+                gradCriterionOut = self.criterion.backward(decOut, batch)  # :334
+                t = self.decoder.backward(batch, gradCriterionOut)         # :335
+                self.encoder.backward(batch, t[1])                         # :337 (t[2] in Lua)
+        return curLoss
+
+    def retrieveBatch(self, batch):                                        # model.lua:344-430
+        if not isinstance(batch, Batch):
+            batch = Batch(batch)
+        return self.engine.retrieve(batch, use_gt=bool(self.params.get("useGt", True)))
+
+    # ---------------------------------------------------------------------------------------------
+    def evaluate(self, dataloader, dtype="val"):                           # model.lua:109-139
+        self.wrapper.evaluate()
+        curLoss, numTokens, n = 0.0, 0, 0
+        numThreads = dataloader.numThreads[dtype]
+        for startId in range(0, numThreads, self.params["batchSize"]):
+            batch = Batch(dataloader.getTestBatch(startId, self.params, dtype))
+            curLoss += self.forwardBackward(batch, True)
+            if self.params["decoder"] == "gen":
+                numTokens += int((batch["answer_out"] > 0).sum())
+            n += 1
+        self.wrapper.training()
+        return curLoss / max(numTokens, 1) if self.params["decoder"] == "gen" else curLoss / max(n, 1)
+
+    def retrieve(self, dataloader, dtype="val"):                           # model.lua:142-189
+        self.wrapper.evaluate()
+        ranks = []
+        numThreads = dataloader.numThreads[dtype]
+        for startId in range(0, numThreads, self.params["batchSize"]):
+            batch = dataloader.getTestBatch(startId, self.params, dtype)
+            ranks.append(self.retrieveBatch(batch).reshape(-1, self.params["maxQuesCount"]))
+        self.wrapper.training()
+        return np.concatenate(ranks, 0)
