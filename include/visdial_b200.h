@@ -166,6 +166,13 @@ int vd_profile_reset(vd_engine* e);
 int vd_launch_count(vd_engine* e, int64_t* n_launches);
 int vd_kernel_stats(vd_engine* e, const char* name, int64_t* launches, double* total_ms,
                     double* total_flops, double* total_bytes);
+/* test hooks: the engine's two dense-contraction primitives on caller-provided DEVICE buffers, routed exactly as
+ * the engine routes them (math mode).  tn: C[m,n] = act(beta*C + bias[n] + sum_k A[m,k] B[n,k]);
+ * atb: C[m,n] += sum_k A[k,m] B[k,n]. */
+int vd_gemm_tn(vd_engine* e, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+               float* C, int64_t ldc, float beta, const float* bias, int32_t act);
+int vd_gemm_atb(vd_engine* e, int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                float* C, int64_t ldc);
 /* flush L2 by writing a scratch buffer larger than L2 (bench hygiene) */
 int vd_flush_l2(vd_engine* e);
 

@@ -1,0 +1,180 @@
+"""Tensor-core (tcgen05 / TF32) path against fp64 numpy and against the oracle.
+
+Stated tolerance for TF32 operands (10-bit mantissa, unit round-off 2^-11, fp32 accumulate): a K-term
+contraction of O(1) terms has absolute error ~ 2^-11 * sqrt(K) * |a||b| in the worst direction; the tests
+bound the max error by 2e-3 * sqrt(K) * rms(a) * rms(b) (GEMM primitives) and by rtol 2e-2 on whole-graph
+losses / gradients after 20-40 recurrent steps.  Integer outputs (ranks) are compared exactly on rows whose
+oracle score gaps exceed the TF32 noise."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import full_params, seg_slices, small_params, torch_batch, torch_params
+from oracle import philox
+from oracle import visdial_oracle as O
+from visdial_b200 import VD_MATH_FP32, VD_MATH_TF32, Batch, Engine, init_parameters
+from visdial_b200._lib import check
+from visdial_b200.synthetic import make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+class Dev:
+    def __init__(self, eng, arr):
+        self.eng, self.shape, self.nbytes = eng, arr.shape, arr.nbytes
+        p = C.c_void_p()
+        check(eng.lib.vd_device_alloc(eng.h, C.byref(p), arr.nbytes))
+        self.p = p
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        check(eng.lib.vd_memcpy_h2d(eng.h, p, a.ctypes.data, a.nbytes))
+
+    def get(self):
+        out = np.empty(self.shape, dtype=np.float32)
+        check(self.eng.lib.vd_memcpy_d2h(self.eng.h, out.ctypes.data, self.p, out.nbytes))
+        return out
+
+    def free(self):
+        check(self.eng.lib.vd_device_free(self.eng.h, self.p))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(small_params("lf-ques", "disc"))
+    yield e
+    e.close()
+
+
+def _tn(eng, mode, A, B, Cin, beta, bias, act):
+    eng.set_math_mode(mode)
+    M, K = A.shape
+    N = B.shape[0]
+    dA, dB, dC = Dev(eng, A), Dev(eng, B), Dev(eng, Cin)
+    dbias = Dev(eng, bias) if bias is not None else None
+    check(eng.lib.vd_gemm_tn(eng.h, M, N, K, dA.p, K, dB.p, K, dC.p, N, beta, dbias.p if dbias else None, act))
+    out = dC.get()
+    for d in (dA, dB, dC) + ((dbias,) if dbias else ()):
+        d.free()
+    return out
+
+
+TN_SHAPES = [(128, 128, 32), (128, 256, 64), (256, 128, 512), (300, 2048, 300), (1000, 512, 2048), (77, 300, 512),
+             (4096, 2048, 512), (129, 520, 812), (3200, 512, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", TN_SHAPES)
+def test_gemm_tn_tf32_vs_fp64(eng, M, N, K):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    got = _tn(eng, VD_MATH_TF32, A, B, np.zeros((M, N), np.float32), 0.0, None, 0)
+    tol = 2e-3 * np.sqrt(K)
+    err = np.abs(got - ref).max()
+    assert err < tol, (err, tol)
+    assert err > 0 or K < 8                      # it really ran in reduced precision, not a silent fp32 fallback
+    got32 = _tn(eng, VD_MATH_FP32, A, B, np.zeros((M, N), np.float32), 0.0, None, 0)
+    assert np.abs(got32 - ref).max() < 2e-5 * np.sqrt(K) * 4
+
+
+def test_gemm_tn_epilogue_bias_beta_tanh(eng):
+    rng = np.random.default_rng(5)
+    M, N, K = 200, 384, 96
+    A = rng.standard_normal((M, K)).astype(np.float32) * 0.2
+    B = rng.standard_normal((N, K)).astype(np.float32) * 0.2
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = np.tanh(1.0 * C0 + bias[None, :] + A.astype(np.float64) @ B.astype(np.float64).T)
+    for mode, tol in ((VD_MATH_TF32, 3e-3), (VD_MATH_FP32, 2e-5)):
+        got = _tn(eng, mode, A, B, C0.copy(), 1.0, bias, 1)
+        assert np.abs(got - ref).max() < tol
+
+
+ATB_SHAPES = [(128, 128, 256), (300, 2048, 4000), (512, 2048, 6400), (512, 512, 333), (64, 300, 1000), (2048, 812, 2560)]
+
+
+@pytest.mark.parametrize("M,N,K", ATB_SHAPES)
+def test_gemm_atb_vs_fp64(eng, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((K, M)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = C0 + A.astype(np.float64).T @ B.astype(np.float64)
+    for mode, tol in ((VD_MATH_TF32, 2e-3 * np.sqrt(K)), (VD_MATH_FP32, 1e-4 * np.sqrt(K))):
+        eng.set_math_mode(mode)
+        dA, dB, dC = Dev(eng, A), Dev(eng, B), Dev(eng, C0)
+        check(eng.lib.vd_gemm_atb(eng.h, M, N, K, dA.p, M, dB.p, N, dC.p, N))
+        got = dC.get()
+        for d in (dA, dB, dC):
+            d.free()
+        assert np.abs(got - ref).max() < tol, mode
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("lf-ques", "gen"), ("hrea-ques-im-hist", "gen"),
+                                     ("lf-ques-im-hist", "disc")])
+def test_tf32_graph_matches_oracle_mid_size(enc, dec):
+    """H=128 so that the fused tcgen05 LSTM kernels (H % 128 == 0) are the ones that run."""
+    p = small_params(enc, dec, rnnHiddenSize=128, embedSize=64, vocabSize=200, numOptions=10, commonEmbeddingSize=64,
+                     imgFeatureSize=64 if "att" in enc else 256, imgSpatialSize=4, imgEmbedSize=32)
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 13, seed=7, max_ques_len=9, max_ans_len=6, max_cap_len=12, max_hist_len=14, max_hist_concat=40,
+                    empty_round_every=4)
+    eng = Engine(p)
+    eng.set_math_mode(VD_MATH_TF32)
+    eng.set_parameters(flat)
+    eng.set_training(1)
+    eng.set_dropout_seed(11, 3)
+    eng.zero_grad()
+    loss = eng.forward_backward(Batch(nb))
+    g = eng.get_gradients()
+    psite = {O.SITE_FUSION: p["dropout"]}
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3, psite), structure="batched"), p,
+                             torch_params(p, flat), torch_batch(nb))
+    assert abs(loss - ref["loss"]) < 5e-3 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
+    for name, s in seg_slices(p).items():
+        r = ref["grads"][name].numpy().ravel()
+        if np.abs(r).max() < 1e-7:
+            continue
+        assert _rel(g[s], r) < 3e-2, name
+    eng.close()
+
+
+def test_tf32_headline_shapes_and_rank_exactness():
+    p = full_params("mn-att-ques-im-hist", "disc")
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 2, seed=5)
+    eng = Engine(p)
+    eng.set_math_mode(VD_MATH_TF32)
+    eng.set_parameters(flat)
+    eng.set_training(1)
+    eng.set_dropout_seed(11, 3)
+    eng.zero_grad()
+    loss = eng.forward_backward(Batch(nb))
+    g = eng.get_gradients()
+    P = torch_params(p, flat)
+    tb = torch_batch(nb)
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3), structure="batched"), p, P, tb)
+    assert abs(loss - ref["loss"]) < 5e-3 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
+    worst = max(_rel(g[s], ref["grads"][n].numpy()) for n, s in seg_slices(p).items())
+    assert worst < 5e-2, worst
+    # ranks: exact wherever the oracle's gap to the neighbouring scores exceeds the TF32 noise (5e-3 abs here)
+    ranks = eng.retrieve(Batch(nb), use_gt=False)
+    ev = O.forward_backward(O.Ctx(structure="batched"), p, P, tb, only_forward=True)
+    sc = ev["decOut"].numpy()
+    ref_r = O.compute_ranks(ev["decOut"]).numpy()
+    gap = np.abs(sc[:, :, None] - sc[:, None, :]) + np.eye(100)[None] * 1e9
+    safe = gap.min(2) > 5e-3                      # (N,100): options whose score is isolated
+    assert safe.mean() > 0.5
+    assert np.array_equal(ranks[safe], ref_r[safe])
+    # argmax (rank-1 option) exact when the top-2 gap is safe
+    srt = np.sort(sc, 1)
+    top_ok = (srt[:, -1] - srt[:, -2]) > 5e-3
+    assert np.array_equal((ranks == 1).argmax(1)[top_ok], sc.argmax(1)[top_ok])
+    eng.close()

@@ -93,6 +93,10 @@ SIGNATURES = {
     "vd_profile_reset": [_H],
     "vd_launch_count": [_H, _P(C.c_int64)],
     "vd_kernel_stats": [_H, C.c_char_p, _P(C.c_int64), _P(C.c_double), _P(C.c_double), _P(C.c_double)],
+    "vd_gemm_tn": [_H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                   C.c_int64, C.c_float, C.c_void_p, C.c_int32],
+    "vd_gemm_atb": [_H, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                    C.c_int64],
     "vd_flush_l2": [_H],
 }
 

@@ -249,6 +249,24 @@ int vd_kernel_stats(vd_engine* h, const char* name, int64_t* launches, double* t
     if (total_bytes) *total_bytes = s.bytes;
   })
 }
+int vd_gemm_tn(vd_engine* h, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+               float* C, int64_t ldc, float beta, const float* bias, int32_t act) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(A && B && C, VD_E_BADARG, "null operand");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    e->gemm_tn(M, N, K, A, lda, nullptr, B, ldb, C, ldc, beta, bias, act);
+  })
+}
+int vd_gemm_atb(vd_engine* h, int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                float* C, int64_t ldc) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(A && B && C, VD_E_BADARG, "null operand");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    e->gemm_atb(M, N, K, A, lda, nullptr, B, ldb, C, ldc);
+  })
+}
 int vd_flush_l2(vd_engine* h) {
   VD_TRY({
     Engine* e = ENG(h);

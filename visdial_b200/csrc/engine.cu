@@ -278,11 +278,22 @@ void Engine::lstm_forward(LstmRun& r, bool save) {
   const float* A = r.x ? r.x : Wp(0);
   const int64_t lda = r.x ? D : cfg.E;
   r.saved = save;
+  // Tensor-core path: the x-projection of an embedding-gathered input becomes a (V+1, 4H) projection table
+  // computed once per forward (E Wx^T: the 300-wide half of every step's contraction collapses into a
+  // gather in the step epilogue); a dense input keeps the batched x-projection.  Each step is then ONE fused
+  // kernel: recurrent tcgen05 GEMM + SeqLSTM pointwise epilogue.
+  const bool tc = math_mode == VD_MATH_TF32 && H % 64 == 0;
+  const float* ptable = nullptr;
+  if (tc && r.gather) {
+    float* pt = arena.get<float>((int64_t)(cfg.V + 1) * G);
+    gemm_tn(cfg.V + 1, G, D, Wp(0), cfg.E, nullptr, WtS, D + H, pt, G, 0.f, nullptr, 0);
+    ptable = pt;
+  }
   if (save) {
     r.h = arena.get<float>((int64_t)r.T * R * H);
     r.c = arena.get<float>((int64_t)r.T * R * H);
     r.gates = arena.get<float>((int64_t)r.T * R * G);
-    gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, nullptr, 0);
+    if (!ptable) gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, nullptr, 0);
   } else {
     r.h = arena.get<float>(2 * R * H);
     r.c = arena.get<float>(2 * R * H);
@@ -293,7 +304,22 @@ void Engine::lstm_forward(LstmRun& r, bool save) {
     float* g = save ? r.gates + (int64_t)t * R * G : r.gates;
     const float* hp = t > 0 ? r.h + pslot * R * H : r.h0;
     const float* cp = t > 0 ? r.c + pslot * R * H : r.c0;
-    LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * (H + (save ? 0 : D)), 4.0 * R * (G + 4.0 * H));
+    LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * (H + ((save && !ptable) ? 0 : D)), 4.0 * R * (G + 4.0 * H));
+    if (tc) {
+      const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
+      int has_x = 0;
+      if (!ptable) {
+        if (!save) {
+          const float* At = r.x + (int64_t)t * R * D;
+          gemm_tn((int)R, G, D, At, lda, nullptr, WtS, D + H, g, G, 0.f, nullptr, 0);
+        }
+        has_x = 1;
+      }
+      if (lstm_step_fwd_tc(cx, R, H, hp, WtS + D, D + H, bias, (save || has_x) ? g : nullptr, has_x, ptable,
+                           ptable ? r.gather + (int64_t)t * R : nullptr, cp, r.c + slot * R * H, r.h + slot * R * H, mk))
+        continue;
+      VD_REQUIRE(false, VD_E_STATE, "lstm_step_fwd_tc refused a shape the engine routed to it");
+    }
     if (!save) {
       const float* At = r.x ? r.x + (int64_t)t * R * D : A;
       gemm_tn((int)R, G, D, At, lda, r.gather ? r.gather + (int64_t)t * R : nullptr, WtS, D + H, g, G, 0.f, nullptr, 0);
@@ -314,7 +340,28 @@ void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last
   float* dc_carry = arena.get<float>(R * H);
   float* dh_rec = arena.get<float>(R * H);
   VD_CUDA_CHECK(cudaMemsetAsync(dc_carry, 0, (size_t)R * H * sizeof(float), cx.stream));
-  for (int t = r.T - 1; t >= 0; --t) {
+  const bool tc = math_mode == VD_MATH_TF32 && H % 128 == 0;
+  if (tc) {
+    // one fused kernel per step: dh_rec = da_{t+1} Wh on tcgen05, backward pointwise in the epilogue
+    if (dc_last) VD_CUDA_CHECK(cudaMemcpyAsync(dc_carry, dc_last, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
+    const float* ext_last = dh_all ? dh_all + (int64_t)(r.T - 1) * R * H : dh_last;
+    if (dh_all && dh_last) {
+      float* tmp = arena.get<float>(R * H);
+      add_out(cx, tmp, dh_all + (int64_t)(r.T - 1) * R * H, dh_last, R * H);
+      ext_last = tmp;
+    }
+    for (int t = r.T - 1; t >= 0; --t) {
+      const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
+      const float* ext = (t == r.T - 1) ? ext_last : (dh_all ? dh_all + (int64_t)t * R * H : nullptr);
+      LaunchCtx::Scope sc(&cx, "lstm_step_bwd", t == r.T - 1 ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
+      bool ok = lstm_step_bwd_tc(cx, R, H, t == r.T - 1 ? nullptr : da + (int64_t)(t + 1) * R * G, Ws + (int64_t)D * G,
+                                 r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, ext, dc_carry,
+                                 r.mask ? r.mask + (int64_t)t * R : nullptr, da + (int64_t)t * R * G);
+      VD_REQUIRE(ok, VD_E_STATE, "lstm_step_bwd_tc refused a shape the engine routed to it");
+    }
+    if (dh0_out) gemm_tn((int)R, H, G, da, G, nullptr, Ws + (int64_t)D * G, G, dh0_out, H, 0.f, nullptr, 0);
+  }
+  for (int t = tc ? -1 : r.T - 1; t >= 0; --t) {
     const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
     const float* rec = (t == r.T - 1) ? dh_last : dh_rec;
     const float* ext = dh_all ? dh_all + (int64_t)t * R * H : nullptr;

@@ -1,9 +1,505 @@
-// tcgen05 / TMEM / TMA dense contractions (TF32 operands, fp32 accumulate).  Placeholder until the
-// tensor-core kernels land: returning false routes the call to the fp32 CUDA-core kernels.
+// Dense contractions on the 5th-gen tensor cores: tcgen05.mma kind::tf32 (fp32 operands in shared memory,
+// TF32 multiply, fp32 accumulate in TMEM), operands staged by TMA (128B-swizzled tiles), one persistent CTA
+// per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2-5 =
+// epilogue (TMEM -> registers -> fused pointwise -> global).  Double-buffered TMEM accumulators let the
+// epilogue of tile i overlap the main loop of tile i+1.
+//
+//   MODE_GENERIC : C = act(beta*C + bias + A B^T)                          (nn.Linear and friends)
+//   MODE_LSTM_FWD: gates = A_h Wh^T (+ x-projection) -> SeqLSTM pointwise   (one launch per time step)
+//   MODE_LSTM_BWD: dh = da_{t+1} Wh -> SeqLSTM backward pointwise -> da_t   (one launch per time step)
+//   k_tc_atb     : C += A^T B with both operands MN-major                   (weight gradients, split-K)
+#include <cuda.h>
+#include <mutex>
 #include "kernels.cuh"
+
 namespace vd {
-bool gemm_tn_tc(LaunchCtx&, int, int, int, const float*, int64_t, const int32_t*, const float*, int64_t, float*, int64_t,
-                float, const float*, int) { return false; }
+namespace tc {
+
+constexpr int BM = 128;          // rows per tile (UMMA M)
+constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
+constexpr int NTHREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+enum { MODE_GENERIC = 0, MODE_LSTM_FWD = 1, MODE_LSTM_BWD = 2 };
+
+struct Params {
+  int M, N, K;                    // GEMM sizes (N = output columns; LSTM_FWD: N = 4H, LSTM_BWD: N = H)
+  int H;
+  // generic
+  float* C; int64_t ldc; float beta; const float* bias; int act;
+  // lstm fwd
+  float* gates;                   // (R,4H): in = x-projection pre-activations (if has_xproj), out = activated gates
+  int has_xproj;
+  const float* ptable; const int32_t* tok;   // optional gathered x-projection: ptable[tok[r], 4H]
+  const float* c_prev; float* c_out; float* h_out; const int32_t* mask_ids;
+  // lstm bwd
+  const float* gsave; const float* c_cur; const float* dh_ext; float* dc_carry; float* da;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;        // version
+  d |= (uint64_t)2 << 61;        // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int BN> struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 4;        // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM;
+        const int nt = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full[s], L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+          if (MODE == MODE_LSTM_FWD) {
+            // interleave the 4 gate blocks of this hidden-unit slice: tile columns = [i | f | o | g]
+            constexpr int HB = BN / 4;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tma_load_2d(sb + g * HB * BK * 4, &tmB, &full[s], kb * BK, g * p.H + nt * HB);
+          } else {
+            tma_load_2d(sb, &tmB, &full[s], kb * BK, nt * BN);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+    int s = 0; uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      mbar_wait(&tempty[buf], bph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t adesc = make_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_tf32(d_tmem, adesc + (uint64_t)(k * UMMA_K * 4 >> 4), bdesc + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
+                      (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      const int m0 = (tile / num_n) * BM;
+      const int nt = tile % num_n;
+      mbar_wait(&tfull[buf], bph);
+      tc_fence_after();
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+
+      if (MODE == MODE_GENERIC) {
+        const int n0 = nt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 8) {
+          if (n0 + c >= p.N) break;                 // warp-uniform
+          float v[8];
+          tmem_ld8(taddr + c, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* crow = p.C + row * p.ldc + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int n = n0 + c + j;
+              if (n < p.N) {
+                float x = v[j];
+                if (p.bias) x += p.bias[n];
+                if (p.beta != 0.f) x += p.beta * crow[j];
+                crow[j] = p.act == 1 ? tanhf(x) : x;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else if (MODE == MODE_LSTM_FWD) {
+        constexpr int HB = BN / 4;
+        const int H = p.H, j0 = nt * HB;
+        const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
+        const float* prow = (row_ok && p.ptable) ? p.ptable + (int64_t)p.tok[row] * 4 * H : nullptr;
+        float* grow = p.gates ? p.gates + row * 4 * H : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < HB; c += 8) {
+          float a[4][8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * HB + c, a[g]);
+          tmem_ld_wait();
+          if (p.K == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[g][e] = 0.f;
+          }
+          if (row_ok) {
+          const int j = j0 + c;
+          float cn[8], hn[8];
+          if (masked) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[0][e] = a[1][e] = a[2][e] = a[3][e] = 0.f; cn[e] = 0.f; hn[e] = 0.f; }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + g * H + j);
+              float4 b0 = b4[0], b1 = b4[1];
+              a[g][0] += b0.x; a[g][1] += b0.y; a[g][2] += b0.z; a[g][3] += b0.w;
+              a[g][4] += b1.x; a[g][5] += b1.y; a[g][6] += b1.z; a[g][7] += b1.w;
+              if (p.has_xproj) {
+                const float4* x4 = reinterpret_cast<const float4*>(grow + g * H + j);
+                float4 x0 = x4[0], x1 = x4[1];
+                a[g][0] += x0.x; a[g][1] += x0.y; a[g][2] += x0.z; a[g][3] += x0.w;
+                a[g][4] += x1.x; a[g][5] += x1.y; a[g][6] += x1.z; a[g][7] += x1.w;
+              }
+              if (prow) {
+                const float4* x4 = reinterpret_cast<const float4*>(prow + g * H + j);
+                float4 x0 = x4[0], x1 = x4[1];
+                a[g][0] += x0.x; a[g][1] += x0.y; a[g][2] += x0.z; a[g][3] += x0.w;
+                a[g][4] += x1.x; a[g][5] += x1.y; a[g][6] += x1.z; a[g][7] += x1.w;
+              }
+            }
+            float cp[8];
+            if (p.c_prev) {
+              const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + row * H + j);
+              float4 c0 = c4[0], c1 = c4[1];
+              cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float gi = sigmoidf_(a[0][e]), gf = sigmoidf_(a[1][e]), go = sigmoidf_(a[2][e]), gg = tanhf(a[3][e]);
+              float c_ = gf * cp[e] + gi * gg;
+              a[0][e] = gi; a[1][e] = gf; a[2][e] = go; a[3][e] = gg;
+              cn[e] = c_; hn[e] = go * tanhf(c_);
+            }
+          }
+          if (grow) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float4* o4 = reinterpret_cast<float4*>(grow + g * H + j);
+              o4[0] = make_float4(a[g][0], a[g][1], a[g][2], a[g][3]);
+              o4[1] = make_float4(a[g][4], a[g][5], a[g][6], a[g][7]);
+            }
+          }
+          float4* co = reinterpret_cast<float4*>(p.c_out + row * H + j);
+          co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          float4* ho = reinterpret_cast<float4*>(p.h_out + row * H + j);
+          ho[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); ho[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+          }
+          __syncwarp();
+        }
+      } else {   // MODE_LSTM_BWD: accumulator = dh_rec for hidden units [nt*BN, nt*BN + BN)
+        const int H = p.H, j0 = nt * BN;
+        const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 8) {
+          float dh[8];
+          tmem_ld8(taddr + c, dh);
+          tmem_ld_wait();
+          if (p.K == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dh[e] = 0.f;
+          }
+          if (row_ok) {
+          const int j = j0 + c;
+          float out[4][8], dcn[8];
+          if (masked) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { out[0][e] = out[1][e] = out[2][e] = out[3][e] = 0.f; dcn[e] = 0.f; }
+          } else {
+            float g[4][8], cp[8], cc[8], dc[8];
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              const float4* x4 = reinterpret_cast<const float4*>(p.gsave + row * 4 * H + gg * H + j);
+              float4 x0 = x4[0], x1 = x4[1];
+              g[gg][0] = x0.x; g[gg][1] = x0.y; g[gg][2] = x0.z; g[gg][3] = x0.w;
+              g[gg][4] = x1.x; g[gg][5] = x1.y; g[gg][6] = x1.z; g[gg][7] = x1.w;
+            }
+            auto ld8 = [&](const float* base, float* dst) {
+              const float4* x4 = reinterpret_cast<const float4*>(base + row * H + j);
+              float4 x0 = x4[0], x1 = x4[1];
+              dst[0] = x0.x; dst[1] = x0.y; dst[2] = x0.z; dst[3] = x0.w; dst[4] = x1.x; dst[5] = x1.y; dst[6] = x1.z; dst[7] = x1.w;
+            };
+            if (p.c_prev) ld8(p.c_prev, cp); else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+            }
+            ld8(p.c_cur, cc);
+            ld8(p.dc_carry, dc);
+            if (p.dh_ext) { float t[8]; ld8(p.dh_ext, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dh[e] += t[e]; }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
+              float tcv = tanhf(cc[e]);
+              float d = dc[e] + dh[e] * go * (1.f - tcv * tcv);
+              out[0][e] = d * gg_ * gi * (1.f - gi);
+              out[1][e] = d * cp[e] * gf * (1.f - gf);
+              out[2][e] = dh[e] * tcv * go * (1.f - go);
+              out[3][e] = d * gi * (1.f - gg_ * gg_);
+              dcn[e] = d * gf;
+            }
+          }
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            float4* o4 = reinterpret_cast<float4*>(p.da + row * 4 * H + gg * H + j);
+            o4[0] = make_float4(out[gg][0], out[gg][1], out[gg][2], out[gg][3]);
+            o4[1] = make_float4(out[gg][4], out[gg][5], out[gg][6], out[gg][7]);
+          }
+          float4* d4 = reinterpret_cast<float4*>(p.dc_carry + row * H + j);
+          d4[0] = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]); d4[1] = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  VD_REQUIRE(fn != nullptr, -3, "cuTensorMapEncodeTiled not available from the driver");
+  return fn;
+}
+
+// 2-D fp32 tensor map: `rows` x `cols` (cols contiguous), row pitch ld floats, box = box_rows x 32 floats, 128B swizzle
+static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = BK) {
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): base %p rows %lld cols %lld ld %lld box %dx%d", (int)r, (void*)base,
+             (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+    throw CudaError(-3, buf);
+  }
+  return tm;
+}
+
+static bool tma_ok(const float* p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
+
+template <int BN, int MODE>
+static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, const Params& p, int num_tiles) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  int grid = std::min(num_tiles, cx.sm_count);
+  k_tc_gemm<BN, MODE><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, p);
+  check_launch(cx, "k_tc_gemm");
+}
+
+}  // namespace tc
+
+// ---- public entry points ------------------------------------------------------------------------
+bool gemm_tn_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda, const int32_t* a_gather, const float* B,
+                int64_t ldb, float* C, int64_t ldc, float beta, const float* bias, int act) {
+  using namespace tc;
+  if (a_gather) return false;                               // gathered rows go through the projection table instead
+  if (M < 64 || N < 16 || K < 32) return false;             // tiny contractions stay on CUDA cores
+  if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
+  Params p = {};
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.beta = beta; p.bias = bias; p.act = act;
+  if (N > 128) {
+    CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 256);
+    launch<256, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 256));
+  } else {
+    CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 128);
+    launch<128, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 128));
+  }
+  return true;
+}
+
 bool gemm_atb_tc(LaunchCtx&, int, int, int64_t, const float*, int64_t, const int32_t*, const float*, int64_t, float*,
                  int64_t) { return false; }
+
+// One SeqLSTM forward step on the tensor cores: gates = h_prev Wh^T (+ xproj | + ptable[tok]) + bias, then the
+// pointwise half, fused.  WtS_h = transposed shadow weight offset to the h columns: [4H, ld] with K = H.
+bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, const float* WtS_h, int64_t ldw, const float* bias,
+                      float* gates, int has_xproj, const float* ptable, const int32_t* tok, const float* c_prev, float* c_out,
+                      float* h_out, const int32_t* mask_ids) {
+  using namespace tc;
+  if (H % 64 != 0 || R < 1) return false;
+  if (!tma_ok(WtS_h, ldw) || (h_prev && !tma_ok(h_prev, H))) return false;
+  Params p = {};
+  p.M = (int)R; p.N = 4 * H; p.K = h_prev ? H : 0; p.H = H;      // K == 0: no recurrent term (t = 0 without h0)
+  if (!h_prev) h_prev = WtS_h;                                      // any valid address for the (unused) tensor map p.bias = bias; p.gates = gates; p.has_xproj = has_xproj; p.ptable = ptable; p.tok = tok;
+  p.c_prev = c_prev; p.c_out = c_out; p.h_out = h_out; p.mask_ids = mask_ids;
+  CUtensorMap tA = make_tmap(h_prev, p.K ? R : 128, H, H, BM), tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
+  launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 64));
+  return true;
+}
+
+// One SeqLSTM backward step: dh_rec = da_next Wh (Wh rows = reference layout rows D.., [H, 4H]) fused with the
+// backward pointwise half producing da_t and the cell-gradient carry.
+bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, const float* Wh, const float* gsave,
+                      const float* c_prev, const float* c_cur, const float* dh_ext, float* dc_carry, const int32_t* mask_ids,
+                      float* da) {
+  using namespace tc;
+  if (H % 128 != 0 || R < 1) return false;
+  if (!tma_ok(Wh, 4 * H) || (da_next && !tma_ok(da_next, 4 * H))) return false;
+  Params p = {};
+  p.M = (int)R; p.N = H; p.K = da_next ? 4 * H : 0; p.H = H;       // K == 0: last time step, no recurrent gradient
+  if (!da_next) da_next = Wh; p.gsave = gsave; p.c_prev = c_prev; p.c_cur = c_cur; p.dh_ext = dh_ext;
+  p.dc_carry = dc_carry; p.mask_ids = mask_ids; p.da = da;
+  CUtensorMap tA = make_tmap(da_next, p.K ? R : 128, 4 * (int64_t)H, 4 * (int64_t)H, BM), tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
+  launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 128));
+  return true;
+}
+
 }  // namespace vd

@@ -111,3 +111,13 @@ void clamp_adam(LaunchCtx& cx, float* W, float* dW, float* m, float* v, int64_t 
 void fill_l2_flush(LaunchCtx& cx, float* buf, int64_t n);
 
 }  // namespace vd
+
+namespace vd {
+// fused SeqLSTM steps on the tensor cores (gemm_tc.cu); return false when the shape is not taken
+bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, const float* WtS_h, int64_t ldw, const float* bias,
+                      float* gates, int has_xproj, const float* ptable, const int32_t* tok, const float* c_prev, float* c_out,
+                      float* h_out, const int32_t* mask_ids);
+bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, const float* Wh, const float* gsave,
+                      const float* c_prev, const float* c_cur, const float* dh_ext, float* dc_carry, const int32_t* mask_ids,
+                      float* da);
+}  // namespace vd

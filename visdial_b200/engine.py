@@ -143,6 +143,8 @@ class Batch:
         b.B, b.Tq = q.shape[0], q.shape[2]
         b.Th = a["hist"].shape[2] if "hist" in a else 0
         b.Ta = a["answer_in"].shape[2] if "answer_in" in a else 0
+        if "options" in a and "option_in" in a:
+            raise ValueError("a batch carries either raw `options` (disc) or `option_in/option_out` (gen eval), not both")
         if "options" in a:
             b.To = a["options"].shape[2]
         elif "option_in" in a:

@@ -109,6 +109,7 @@ def make_batch(params: dict, B: int, seed: int = 1234, max_ques_len: int = 20, m
         np.put_along_axis(oo, olen[:, :, None], END, axis=2)
         out["option_in"] = oi.reshape(B, R, K, To2)
         out["option_out"] = oo.reshape(B, R, K, To2)
+        del out["options"]          # the dataloader emits either raw options (disc) or option_in/out (gen eval)
     return out
 
 
