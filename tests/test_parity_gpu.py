@@ -190,11 +190,10 @@ def test_headline_shapes_against_oracle_fp32():
     ref_r = O.retrieve_batch(O.Ctx(structure="batched"), p, torch_params(p, flat), torch_batch(nb), use_gt=False).numpy()
     # ranks are exact wherever the oracle's score gap to the neighbours exceeds the fp32 noise floor
     sc = O.forward_backward(O.Ctx(structure="batched"), p, torch_params(p, flat), torch_batch(nb), only_forward=True)["decOut"].numpy()
-    srt = np.sort(sc, 1)
-    min_gap = np.diff(srt, axis=1).min(1)
-    ok = min_gap > 1e-4
-    assert ok.sum() >= 0.8 * len(ok)
-    assert np.array_equal(ranks[ok], ref_r[ok])
+    gap = np.abs(sc[:, :, None] - sc[:, None, :]) + np.eye(100)[None] * 1e9
+    safe = gap.min(2) > 2e-5                      # options whose score is isolated from every other option
+    assert safe.mean() > 0.9
+    assert np.array_equal(ranks[safe], ref_r[safe])
     eng.close()
 
 

@@ -1,8 +1,9 @@
 """Tensor-core (tcgen05 / TF32) path against fp64 numpy and against the oracle.
 
 Stated tolerance for TF32 operands (10-bit mantissa, unit round-off 2^-11, fp32 accumulate): a K-term
-contraction of O(1) terms has absolute error ~ 2^-11 * sqrt(K) * |a||b| in the worst direction; the tests
-bound the max error by 2e-3 * sqrt(K) * rms(a) * rms(b) (GEMM primitives) and by rtol 2e-2 on whole-graph
+contraction of O(1) terms: the tensor core TRUNCATES fp32 operands to TF32 (relative error < 2^-10 per operand),
+so a K-term contraction of unit-variance operands has rms error ~ 1e-3 * sqrt(K); the tests bound the rms error
+by 1.5e-3 * sqrt(K) and the max error by 8e-3 * sqrt(K) (GEMM primitives) and use rtol 3e-2 on whole-graph
 losses / gradients after 20-40 recurrent steps.  Integer outputs (ranks) are compared exactly on rows whose
 oracle score gaps exceed the TF32 noise."""
 import ctypes as C
@@ -70,9 +71,9 @@ def test_gemm_tn_tf32_vs_fp64(eng, M, N, K):
     B = rng.standard_normal((N, K)).astype(np.float32)
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     got = _tn(eng, VD_MATH_TF32, A, B, np.zeros((M, N), np.float32), 0.0, None, 0)
-    tol = 2e-3 * np.sqrt(K)
     err = np.abs(got - ref).max()
-    assert err < tol, (err, tol)
+    rms = float(np.sqrt(np.mean((got - ref) ** 2)))
+    assert err < 8e-3 * np.sqrt(K) and rms < 1.5e-3 * np.sqrt(K), (err, rms)
     assert err > 0 or K < 8                      # it really ran in reduced precision, not a silent fp32 fallback
     got32 = _tn(eng, VD_MATH_FP32, A, B, np.zeros((M, N), np.float32), 0.0, None, 0)
     assert np.abs(got32 - ref).max() < 2e-5 * np.sqrt(K) * 4
@@ -86,7 +87,7 @@ def test_gemm_tn_epilogue_bias_beta_tanh(eng):
     C0 = rng.standard_normal((M, N)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
     ref = np.tanh(1.0 * C0 + bias[None, :] + A.astype(np.float64) @ B.astype(np.float64).T)
-    for mode, tol in ((VD_MATH_TF32, 3e-3), (VD_MATH_FP32, 2e-5)):
+    for mode, tol in ((VD_MATH_TF32, 1e-2), (VD_MATH_FP32, 2e-5)):
         got = _tn(eng, mode, A, B, C0.copy(), 1.0, bias, 1)
         assert np.abs(got - ref).max() < tol
 
@@ -101,7 +102,7 @@ def test_gemm_atb_vs_fp64(eng, M, N, K):
     B = rng.standard_normal((K, N)).astype(np.float32)
     C0 = rng.standard_normal((M, N)).astype(np.float32)
     ref = C0 + A.astype(np.float64).T @ B.astype(np.float64)
-    for mode, tol in ((VD_MATH_TF32, 2e-3 * np.sqrt(K)), (VD_MATH_FP32, 1e-4 * np.sqrt(K))):
+    for mode, tol in ((VD_MATH_TF32, 8e-3 * np.sqrt(K)), (VD_MATH_FP32, 1e-4 * np.sqrt(K))):
         eng.set_math_mode(mode)
         dA, dB, dC = Dev(eng, A), Dev(eng, B), Dev(eng, C0)
         check(eng.lib.vd_gemm_atb(eng.h, M, N, K, dA.p, M, dB.p, N, dC.p, N))

@@ -377,7 +377,14 @@ void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last
   float* dWs = dWp(r.wseg);
   const float* A = r.x ? r.x : Wp(0);
   const int64_t lda = r.x ? D : cfg.E;
-  gemm_atb(D, G, TR, A, lda, r.gather, da, G, dWs, G);
+  const int32_t* gat = r.gather;
+  if (!r.x && math_mode == VD_MATH_TF32) {
+    // TMA cannot gather rows: materialise the embedded tokens once (T*R*E floats, HBM-cheap) for the tensor-core GEMM
+    float* xm = arena.get<float>(TR * D);
+    embed_rows(cx, xm, Wp(0), r.gather, TR, D, dropcfg(0.f), 0);
+    A = xm; gat = nullptr;
+  }
+  gemm_atb(D, G, TR, A, lda, gat, da, G, dWs, G);
   if (r.T > 1) gemm_atb(H, G, TR - R, r.h, H, nullptr, da + R * G, G, dWs + (int64_t)D * G, G);
   if (r.h0) gemm_atb(H, G, R, r.h0, H, nullptr, da, G, dWs + (int64_t)D * G, G);
   colsum_add(cx, dWp(r.wseg + 1), da, TR, G, G);

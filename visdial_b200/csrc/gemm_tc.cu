@@ -50,12 +50,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
+  uint32_t done = 0, spins = 0;
   uint32_t addr = smem_u32(bar);
   while (!done) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();     // watchdog: a protocol bug must fault, not hang the GPU
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -201,6 +202,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      if (num_kb == 0 && lane == 0) mbar_arrive(&tfull[buf]);     // K == 0: nothing to wait for, release the epilogue
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -391,6 +394,125 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradients: C[M,N] += sum_k A[k,m] B[k,n].  Both operands are "MN-major" (the contraction index k is
+// the row index of the activations in HBM): a TMA box of 32 columns x KB rows lands in shared memory as KB rows
+// of 128 bytes (128B swizzle), which is exactly the canonical MN-major SW128 UMMA layout — 8 k-rows per 1024-byte
+// atom (one tf32 MMA consumes one atom), 32-column groups LBO bytes apart.  One (tile, K-split) per CTA; the
+// fp32 partial sums are reduced into C with vector red.global.add.
+constexpr int ATB_KB = 32;       // k-rows per pipeline stage (4 MMAs)
+constexpr int ATB_BN = 256;
+struct AtbParams { int M, N; int64_t K, k_per_split; float* C; int64_t ldc; };
+struct AtbSmem {
+  static constexpr int A_BYTES = BM * ATB_KB * 4;         // 4 boxes of [32 rows x 128 B]
+  static constexpr int B_BYTES = ATB_BN * ATB_KB * 4;     // 8 boxes
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 4;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc_atb(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AtbParams p) {
+  using L = AtbSmem;
+  constexpr int STAGES = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_n = (p.N + ATB_BN - 1) / ATB_BN;
+  const int m0 = (blockIdx.x / num_n) * BM, n0 = (blockIdx.x % num_n) * ATB_BN;
+  const int64_t kbeg = (int64_t)blockIdx.y * p.k_per_split;
+  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+  const int num_kb = (int)((kend - kbeg + ATB_KB - 1) / ATB_KB);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, ATB_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_expect_tx(&full[s], L::STAGE_BYTES);
+        const int krow = (int)(kbeg + (int64_t)kb * ATB_KB);
+        // rows beyond kend but inside the tensor would pollute the sum: the host makes k_per_split a multiple of
+        // ATB_KB, so only the global tail (zero-filled by TMA) can be partial.
+#pragma unroll
+        for (int g = 0; g < BM / 32; ++g) tma_load_2d(sa + g * ATB_KB * 128, &tmA, &full[s], m0 + g * 32, krow);
+#pragma unroll
+        for (int g = 0; g < ATB_BN / 32; ++g) tma_load_2d(sb + g * ATB_KB * 128, &tmB, &full[s], n0 + g * 32, krow);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(BM, ATB_BN, 1, 1);
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATB_KB / UMMA_K; ++k) {
+          const uint64_t adesc = make_desc(sa + k * 1024, ATB_KB * 128, 1024);
+          const uint64_t bdesc = make_desc(sb + k * 1024, ATB_KB * 128, 1024);
+          umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (kb == num_kb - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < ATB_BN; c += 8) {
+      if (n0 + c >= p.N) break;
+      float v[8];
+      tmem_ld8(taddr + c, v);
+      tmem_ld_wait();
+      if (m < p.M) {
+        float* crow = p.C + (int64_t)m * p.ldc + n0 + c;
+        if (n0 + c + 8 <= p.N && ((p.ldc & 3) == 0)) {
+          red_add_v4(crow, v[0], v[1], v[2], v[3]);
+          red_add_v4(crow + 4, v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + c + j < p.N) atomicAdd(crow + j, v[j]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, ATB_BN); }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -465,8 +587,28 @@ bool gemm_tn_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda,
   return true;
 }
 
-bool gemm_atb_tc(LaunchCtx&, int, int, int64_t, const float*, int64_t, const int32_t*, const float*, int64_t, float*,
-                 int64_t) { return false; }
+bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t lda, const int32_t* a_gather, const float* B,
+                 int64_t ldb, float* C, int64_t ldc) {
+  using namespace tc;
+  if (a_gather) return false;
+  if (M < 32 || N < 32 || K < 64) return false;
+  if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
+  const int tiles = cdiv(M, BM) * cdiv(N, ATB_BN);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>((2LL * cx.sm_count + tiles - 1) / tiles, K / (ATB_KB * 4)));
+  int64_t kps = ((K + splits - 1) / splits + ATB_KB - 1) / ATB_KB * ATB_KB;
+  splits = (K + kps - 1) / kps;
+  AtbParams p = {M, N, K, kps, C, ldc};
+  CUtensorMap tA = make_tmap(A, K, M, lda, ATB_KB, 32), tB = make_tmap(B, K, N, ldb, ATB_KB, 32);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_atb, cudaFuncAttributeMaxDynamicSharedMemorySize, AtbSmem::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(tiles, (unsigned)splits);
+  k_tc_atb<<<grid, NTHREADS, AtbSmem::TOTAL, cx.stream>>>(tA, tB, p);
+  check_launch(cx, "k_tc_atb");
+  return true;
+}
 
 // One SeqLSTM forward step on the tensor cores: gates = h_prev Wh^T (+ xproj | + ptable[tok]) + bias, then the
 // pointwise half, fused.  WtS_h = transposed shadow weight offset to the h columns: [4H, ld] with K = H.
