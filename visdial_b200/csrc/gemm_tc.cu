@@ -92,13 +92,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;        // version
-  d |= (uint64_t)2 << 61;        // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32
@@ -397,8 +397,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ------------------------------------------------------------------------------------------------
 // Weight gradients: C[M,N] += sum_k A[k,m] B[k,n].  Both operands are "MN-major" (the contraction index k is
 // the row index of the activations in HBM): a TMA box of 32 columns x KB rows lands in shared memory as KB rows
-// of 128 bytes (128B swizzle), which is exactly the canonical MN-major SW128 UMMA layout — 8 k-rows per 1024-byte
-// atom (one tf32 MMA consumes one atom), 32-column groups LBO bytes apart.  One (tile, K-split) per CTA; the
+// of 128 bytes; with the 128B_ATOM_32B swizzle this is the canonical MN-major SWIZZLE_128B_BASE32B UMMA layout, the only
+// MN-major layout tf32 operands may use (4 k-rows per 512-byte atom, SBO = 512; one K=8 MMA consumes two atoms;
+// 32-column groups are LBO bytes apart).  One (tile, K-split) per CTA; the
 // fp32 partial sums are reduced into C with vector red.global.add.
 constexpr int ATB_KB = 32;       // k-rows per pipeline stage (4 MMAs)
 constexpr int ATB_BN = 256;
@@ -472,8 +473,8 @@ k_tc_atb(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
         for (int k = 0; k < ATB_KB / UMMA_K; ++k) {
-          const uint64_t adesc = make_desc(sa + k * 1024, ATB_KB * 128, 1024);
-          const uint64_t bdesc = make_desc(sb + k * 1024, ATB_KB * 128, 1024);
+          const uint64_t adesc = make_desc(sa + k * 1024, ATB_KB * 128, 512, 1);
+          const uint64_t bdesc = make_desc(sb + k * 1024, ATB_KB * 128, 512, 1);
           umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
         }
         umma_commit(&empty[s]);
@@ -533,14 +534,15 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D fp32 tensor map: `rows` x `cols` (cols contiguous), row pitch ld floats, box = box_rows x 32 floats, 128B swizzle
-static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = BK) {
+static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = BK,
+                             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap tm;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -598,7 +600,8 @@ bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t
   int64_t kps = ((K + splits - 1) / splits + ATB_KB - 1) / ATB_KB * ATB_KB;
   splits = (K + kps - 1) / kps;
   AtbParams p = {M, N, K, kps, C, ldc};
-  CUtensorMap tA = make_tmap(A, K, M, lda, ATB_KB, 32), tB = make_tmap(B, K, N, ldb, ATB_KB, 32);
+  CUtensorMap tA = make_tmap(A, K, M, lda, ATB_KB, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
+              tB = make_tmap(B, K, N, ldb, ATB_KB, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   static bool attr_set = false;
   if (!attr_set) {
     VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_atb, cudaFuncAttributeMaxDynamicSharedMemorySize, AtbSmem::TOTAL));
@@ -620,7 +623,8 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
   if (!tma_ok(WtS_h, ldw) || (h_prev && !tma_ok(h_prev, H))) return false;
   Params p = {};
   p.M = (int)R; p.N = 4 * H; p.K = h_prev ? H : 0; p.H = H;      // K == 0: no recurrent term (t = 0 without h0)
-  if (!h_prev) h_prev = WtS_h;                                      // any valid address for the (unused) tensor map p.bias = bias; p.gates = gates; p.has_xproj = has_xproj; p.ptable = ptable; p.tok = tok;
+  if (!h_prev) h_prev = WtS_h;                                      // any valid address for the (unused) tensor map
+  p.bias = bias; p.gates = gates; p.has_xproj = has_xproj; p.ptable = ptable; p.tok = tok;
   p.c_prev = c_prev; p.c_out = c_out; p.h_out = h_out; p.mask_ids = mask_ids;
   CUtensorMap tA = make_tmap(h_prev, p.K ? R : 128, H, H, BM), tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
   launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 64));
