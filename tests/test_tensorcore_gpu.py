@@ -163,8 +163,10 @@ def test_tf32_headline_shapes_and_rank_exactness():
     tb = torch_batch(nb)
     ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3), structure="batched"), p, P, tb)
     assert abs(loss - ref["loss"]) < 5e-3 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
-    worst = max(_rel(g[s], ref["grads"][n].numpy()) for n, s in seg_slices(p).items())
-    assert worst < 5e-2, worst
+    # san.hop1.score.bias has a mathematically zero gradient (softmax shift invariance): skip ~0 segments
+    worst = max(_rel(g[s], ref["grads"][n].numpy()) for n, s in seg_slices(p).items()
+                if float(ref["grads"][n].abs().max()) > 1e-6)
+    assert worst < 2e-2, worst
     # ranks: exact wherever the oracle's gap to the neighbouring scores exceeds the TF32 noise (5e-3 abs here)
     ranks = eng.retrieve(Batch(nb), use_gt=False)
     ev = O.forward_backward(O.Ctx(structure="batched"), p, P, tb, only_forward=True)
