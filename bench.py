@@ -224,7 +224,11 @@ def run_ours(args, rank, local, world):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, wall_dev, launches = timed(dev_loader, args.steps, True)
+    if args.ncu_range:                      # `ncu --profile-from-start off`: profile exactly the timed steps
+        eng.profiler_range(True)
+    ms_dev, wall_dev, launches = timed(dev_loader, args.steps, not args.ncu_range)
+    if args.ncu_range:
+        eng.profiler_range(False)
     stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS + ("gemm", "gemm_wgrad", "allreduce")}
     ms_e2e, wall_e2e, _ = timed(host_loader, args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
@@ -282,6 +286,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--ref-batch", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

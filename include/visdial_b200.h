@@ -173,6 +173,8 @@ int vd_gemm_tn(vd_engine* e, int32_t M, int32_t N, int32_t K, const float* A, in
                float* C, int64_t ldc, float beta, const float* bias, int32_t act);
 int vd_gemm_atb(vd_engine* e, int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
                 float* C, int64_t ldc);
+/* cudaProfilerStart / cudaProfilerStop (ncu --profile-from-start off) */
+int vd_profiler_range(vd_engine* e, int32_t start);
 /* flush L2 by writing a scratch buffer larger than L2 (bench hygiene) */
 int vd_flush_l2(vd_engine* e);
 

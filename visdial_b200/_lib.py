@@ -97,6 +97,7 @@ SIGNATURES = {
                    C.c_int64, C.c_float, C.c_void_p, C.c_int32],
     "vd_gemm_atb": [_H, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                     C.c_int64],
+    "vd_profiler_range": [_H, C.c_int32],
     "vd_flush_l2": [_H],
 }
 

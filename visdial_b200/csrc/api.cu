@@ -2,6 +2,7 @@
 // leaves the message in a thread-local buffer (vd_last_error).
 #include "engine.h"
 #include <string.h>
+#include <cuda_profiler_api.h>
 
 namespace vd {
 void comm_unique_id(void* out);
@@ -265,6 +266,13 @@ int vd_gemm_atb(vd_engine* h, int32_t M, int32_t N, int64_t K, const float* A, i
     VD_REQUIRE(A && B && C, VD_E_BADARG, "null operand");
     VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
     e->gemm_atb(M, N, K, A, lda, nullptr, B, ldb, C, ldc);
+  })
+}
+int vd_profiler_range(vd_engine* h, int32_t start) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+    if (start) VD_CUDA_CHECK(cudaProfilerStart()); else VD_CUDA_CHECK(cudaProfilerStop());
   })
 }
 int vd_flush_l2(vd_engine* h) {

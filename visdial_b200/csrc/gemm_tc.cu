@@ -1,6 +1,6 @@
 // Dense contractions on the 5th-gen tensor cores: tcgen05.mma kind::tf32 (fp32 operands in shared memory,
 // TF32 multiply, fp32 accumulate in TMEM), operands staged by TMA (128B-swizzled tiles), one persistent CTA
-// per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2-5 =
+// per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2-9 =
 // epilogue (TMEM -> registers -> fused pointwise -> global).  Double-buffered TMEM accumulators let the
 // epilogue of tile i overlap the main loop of tile i+1.
 //
@@ -18,8 +18,8 @@ namespace tc {
 constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
-constexpr int NTHREADS = 192;
-constexpr int EPI_WARP0 = 2;
+constexpr int EPI_WARPS = 8;     // 2 warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 
 enum { MODE_GENERIC = 0, MODE_LSTM_FWD = 1, MODE_LSTM_BWD = 2 };
 
@@ -91,13 +91,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1 (Blackwell)
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;        // version
+  d |= (uint64_t)1 << 46;             // version
   d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
   return d;
 }
@@ -107,7 +107,30 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Activations of the tensor-core path: ex2.approx / rcp.approx based (abs error ~1e-7, far below the TF32 operand
+// rounding of the contraction they follow).  The fp32 verification path (pointwise.cu) keeps expf / tanhf.
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) {
+  float e = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+__device__ __forceinline__ void ld8(const float* p, float* d) {
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(p)), x1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  d[0] = x0.x; d[1] = x0.y; d[2] = x0.z; d[3] = x0.w; d[4] = x1.x; d[5] = x1.y; d[6] = x1.z; d[7] = x1.w;
+}
+__device__ __forceinline__ void add8(const float* p, float* d) {
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(p)), x1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  d[0] += x0.x; d[1] += x0.y; d[2] += x0.z; d[3] += x0.w; d[4] += x1.x; d[5] += x1.y; d[6] += x1.z; d[7] += x1.w;
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+// streaming store: saved activations are not read again before the backward pass — keep them out of L2's way
+__device__ __forceinline__ void st8_cs(float* p, const float* v) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
 
 template <int BN> struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;        // 16 KB
@@ -115,6 +138,7 @@ template <int BN> struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -139,10 +163,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -206,8 +230,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -223,7 +248,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (MODE == MODE_GENERIC) {
         const int n0 = nt * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 8) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
           if (n0 + c >= p.N) break;                 // warp-uniform
           float v[8];
           tmem_ld8(taddr + c, v);
@@ -235,87 +260,63 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const int n = n0 + c + j;
               if (n < p.N) {
                 float x = v[j];
-                if (p.bias) x += p.bias[n];
+                if (p.bias) x += __ldg(p.bias + n);
                 if (p.beta != 0.f) x += p.beta * crow[j];
-                crow[j] = p.act == 1 ? tanhf(x) : x;
+                crow[j] = p.act == 1 ? ftanh(x) : x;
               }
             }
           }
           __syncwarp();
         }
       } else if (MODE == MODE_LSTM_FWD) {
-        constexpr int HB = BN / 4;
+        constexpr int HB = BN / 4;                  // hidden units per tile
         const int H = p.H, j0 = nt * HB;
         const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
         const float* prow = (row_ok && p.ptable) ? p.ptable + (int64_t)p.tok[row] * 4 * H : nullptr;
         float* grow = p.gates ? p.gates + row * 4 * H : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < HB; c += 8) {
-          float a[4][8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * HB + c, a[g]);
-          tmem_ld_wait();
-          if (p.K == 0) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[g][e] = 0.f;
-          }
-          if (row_ok) {
+        for (int c = half * (HB / 2); c < (half + 1) * (HB / 2); c += 8) {
           const int j = j0 + c;
-          float cn[8], hn[8];
-          if (masked) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { a[0][e] = a[1][e] = a[2][e] = a[3][e] = 0.f; cn[e] = 0.f; hn[e] = 0.f; }
-          } else {
+          float a[4][8], x[4][8], cp[8];
+          // issue the global loads first so that they overlap the TMEM read
+          if (row_ok && !masked) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + g * H + j);
-              float4 b0 = b4[0], b1 = b4[1];
-              a[g][0] += b0.x; a[g][1] += b0.y; a[g][2] += b0.z; a[g][3] += b0.w;
-              a[g][4] += b1.x; a[g][5] += b1.y; a[g][6] += b1.z; a[g][7] += b1.w;
-              if (p.has_xproj) {
-                const float4* x4 = reinterpret_cast<const float4*>(grow + g * H + j);
-                float4 x0 = x4[0], x1 = x4[1];
-                a[g][0] += x0.x; a[g][1] += x0.y; a[g][2] += x0.z; a[g][3] += x0.w;
-                a[g][4] += x1.x; a[g][5] += x1.y; a[g][6] += x1.z; a[g][7] += x1.w;
-              }
-              if (prow) {
-                const float4* x4 = reinterpret_cast<const float4*>(prow + g * H + j);
-                float4 x0 = x4[0], x1 = x4[1];
-                a[g][0] += x0.x; a[g][1] += x0.y; a[g][2] += x0.z; a[g][3] += x0.w;
-                a[g][4] += x1.x; a[g][5] += x1.y; a[g][6] += x1.z; a[g][7] += x1.w;
-              }
+              ld8(p.bias + g * H + j, x[g]);
+              if (p.has_xproj) add8(grow + g * H + j, x[g]);
+              if (prow) add8(prow + g * H + j, x[g]);
             }
-            float cp[8];
-            if (p.c_prev) {
-              const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + row * H + j);
-              float4 c0 = c4[0], c1 = c4[1];
-              cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
-            } else {
+            if (p.c_prev) ld8(p.c_prev + row * H + j, cp);
+            else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) cp[e] = 0.f;
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float gi = sigmoidf_(a[0][e]), gf = sigmoidf_(a[1][e]), go = sigmoidf_(a[2][e]), gg = tanhf(a[3][e]);
-              float c_ = gf * cp[e] + gi * gg;
-              a[0][e] = gi; a[1][e] = gf; a[2][e] = go; a[3][e] = gg;
-              cn[e] = c_; hn[e] = go * tanhf(c_);
-            }
           }
-          if (grow) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float4* o4 = reinterpret_cast<float4*>(grow + g * H + j);
-              o4[0] = make_float4(a[g][0], a[g][1], a[g][2], a[g][3]);
-              o4[1] = make_float4(a[g][4], a[g][5], a[g][6], a[g][7]);
+          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * HB + c, a[g]);
+          tmem_ld_wait();
+          if (row_ok) {
+            float cn[8], hn[8];
+            if (masked) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { a[0][e] = a[1][e] = a[2][e] = a[3][e] = 0.f; cn[e] = 0.f; hn[e] = 0.f; }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float zi = (p.K ? a[0][e] : 0.f) + x[0][e], zf = (p.K ? a[1][e] : 0.f) + x[1][e];
+                const float zo = (p.K ? a[2][e] : 0.f) + x[2][e], zg = (p.K ? a[3][e] : 0.f) + x[3][e];
+                const float gi = fsigmoid(zi), gf = fsigmoid(zf), go = fsigmoid(zo), gg = ftanh(zg);
+                const float c_ = gf * cp[e] + gi * gg;
+                a[0][e] = gi; a[1][e] = gf; a[2][e] = go; a[3][e] = gg;
+                cn[e] = c_; hn[e] = go * ftanh(c_);
+              }
             }
-          }
-          float4* co = reinterpret_cast<float4*>(p.c_out + row * H + j);
-          co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
-          float4* ho = reinterpret_cast<float4*>(p.h_out + row * H + j);
-          ho[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); ho[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            if (grow) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) st8_cs(grow + g * H + j, a[g]);
+            }
+            st8(p.c_out + row * H + j, cn);
+            st8(p.h_out + row * H + j, hn);
           }
           __syncwarp();
         }
@@ -323,63 +324,49 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int H = p.H, j0 = nt * BN;
         const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 8) {
-          float dh[8];
-          tmem_ld8(taddr + c, dh);
-          tmem_ld_wait();
-          if (p.K == 0) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dh[e] = 0.f;
-          }
-          if (row_ok) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
           const int j = j0 + c;
-          float out[4][8], dcn[8];
-          if (masked) {
+          float dh[8], g[4][8], cp[8], cc[8], dc[8], ex[8];
+          if (row_ok && !masked) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { out[0][e] = out[1][e] = out[2][e] = out[3][e] = 0.f; dcn[e] = 0.f; }
-          } else {
-            float g[4][8], cp[8], cc[8], dc[8];
-#pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-              const float4* x4 = reinterpret_cast<const float4*>(p.gsave + row * 4 * H + gg * H + j);
-              float4 x0 = x4[0], x1 = x4[1];
-              g[gg][0] = x0.x; g[gg][1] = x0.y; g[gg][2] = x0.z; g[gg][3] = x0.w;
-              g[gg][4] = x1.x; g[gg][5] = x1.y; g[gg][6] = x1.z; g[gg][7] = x1.w;
-            }
-            auto ld8 = [&](const float* base, float* dst) {
-              const float4* x4 = reinterpret_cast<const float4*>(base + row * H + j);
-              float4 x0 = x4[0], x1 = x4[1];
-              dst[0] = x0.x; dst[1] = x0.y; dst[2] = x0.z; dst[3] = x0.w; dst[4] = x1.x; dst[5] = x1.y; dst[6] = x1.z; dst[7] = x1.w;
-            };
-            if (p.c_prev) ld8(p.c_prev, cp); else {
+            for (int gg = 0; gg < 4; ++gg) ld8(p.gsave + row * 4 * H + gg * H + j, g[gg]);
+            if (p.c_prev) ld8(p.c_prev + row * H + j, cp);
+            else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) cp[e] = 0.f;
             }
-            ld8(p.c_cur, cc);
-            ld8(p.dc_carry, dc);
-            if (p.dh_ext) { float t[8]; ld8(p.dh_ext, t);
+            ld8(p.c_cur + row * H + j, cc);
+            ld8(p.dc_carry + row * H + j, dc);
+            if (p.dh_ext) ld8(p.dh_ext + row * H + j, ex);
+            else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) dh[e] += t[e]; }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
-              float tcv = tanhf(cc[e]);
-              float d = dc[e] + dh[e] * go * (1.f - tcv * tcv);
-              out[0][e] = d * gg_ * gi * (1.f - gi);
-              out[1][e] = d * cp[e] * gf * (1.f - gf);
-              out[2][e] = dh[e] * tcv * go * (1.f - go);
-              out[3][e] = d * gi * (1.f - gg_ * gg_);
-              dcn[e] = d * gf;
+              for (int e = 0; e < 8; ++e) ex[e] = 0.f;
             }
           }
+          tmem_ld8(taddr + c, dh);
+          tmem_ld_wait();
+          if (row_ok) {
+            float out[4][8], dcn[8];
+            if (masked) {
 #pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {
-            float4* o4 = reinterpret_cast<float4*>(p.da + row * 4 * H + gg * H + j);
-            o4[0] = make_float4(out[gg][0], out[gg][1], out[gg][2], out[gg][3]);
-            o4[1] = make_float4(out[gg][4], out[gg][5], out[gg][6], out[gg][7]);
-          }
-          float4* d4 = reinterpret_cast<float4*>(p.dc_carry + row * H + j);
-          d4[0] = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]); d4[1] = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+              for (int e = 0; e < 8; ++e) { out[0][e] = out[1][e] = out[2][e] = out[3][e] = 0.f; dcn[e] = 0.f; }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float dhe = (p.K ? dh[e] : 0.f) + ex[e];
+                const float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
+                const float tcv = ftanh(cc[e]);
+                const float d = dc[e] + dhe * go * (1.f - tcv * tcv);
+                out[0][e] = d * gg_ * gi * (1.f - gi);
+                out[1][e] = d * cp[e] * gf * (1.f - gf);
+                out[2][e] = dhe * tcv * go * (1.f - go);
+                out[3][e] = d * gi * (1.f - gg_ * gg_);
+                dcn[e] = d * gf;
+              }
+            }
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) st8(p.da + row * 4 * H + gg * H + j, out[gg]);
+            st8(p.dc_carry + row * H + j, dcn);
           }
           __syncwarp();
         }
@@ -391,18 +378,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradients: C[M,N] += sum_k A[k,m] B[k,n].  Both operands are "MN-major" (the contraction index k is
 // the row index of the activations in HBM): a TMA box of 32 columns x KB rows lands in shared memory as KB rows
-// of 128 bytes; with the 128B_ATOM_32B swizzle this is the canonical MN-major SWIZZLE_128B_BASE32B UMMA layout, the only
-// MN-major layout tf32 operands may use (4 k-rows per 512-byte atom, SBO = 512; one K=8 MMA consumes two atoms;
-// 32-column groups are LBO bytes apart).  One (tile, K-split) per CTA; the
-// fp32 partial sums are reduced into C with vector red.global.add.
+// of 128 bytes; with the 128B_ATOM_32B swizzle this is the canonical MN-major SWIZZLE_128B_BASE32B UMMA layout, the
+// only MN-major layout tf32 operands may use (4 k-rows per 512-byte atom, SBO = 512; one K=8 MMA consumes two
+// atoms; 32-column groups are LBO bytes apart).  One (tile, K-split) per CTA; the fp32 partial sums are reduced
+// into C with vector red.global.add.
 constexpr int ATB_KB = 32;       // k-rows per pipeline stage (4 MMAs)
 constexpr int ATB_BN = 256;
+constexpr int ATB_THREADS = 192;
 struct AtbParams { int M, N; int64_t K, k_per_split; float* C; int64_t ldc; };
 struct AtbSmem {
   static constexpr int A_BYTES = BM * ATB_KB * 4;         // 4 boxes of [32 rows x 128 B]
@@ -416,7 +404,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(ATB_THREADS, 1)
 k_tc_atb(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AtbParams p) {
   using L = AtbSmem;
   constexpr int STAGES = L::STAGES;
@@ -453,8 +441,7 @@ k_tc_atb(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         uint8_t* sb = sa + L::A_BYTES;
         mbar_expect_tx(&full[s], L::STAGE_BYTES);
         const int krow = (int)(kbeg + (int64_t)kb * ATB_KB);
-        // rows beyond kend but inside the tensor would pollute the sum: the host makes k_per_split a multiple of
-        // ATB_KB, so only the global tail (zero-filled by TMA) can be partial.
+        // k_per_split is a multiple of ATB_KB, so only the global K tail (zero-filled by TMA) can be partial
 #pragma unroll
         for (int g = 0; g < BM / 32; ++g) tma_load_2d(sa + g * ATB_KB * 128, &tmA, &full[s], m0 + g * 32, krow);
 #pragma unroll
@@ -533,7 +520,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor map: `rows` x `cols` (cols contiguous), row pitch ld floats, box = box_rows x 32 floats, 128B swizzle
+// 2-D fp32 tensor map: `rows` x `cols` (cols contiguous), row pitch ld floats, box = box_rows x box_cols floats
 static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = BK,
                              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap tm;
@@ -579,12 +566,16 @@ bool gemm_tn_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda,
   if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
   Params p = {};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.beta = beta; p.bias = bias; p.act = act;
-  if (N > 128) {
+  const int tiles256 = cdiv(M, BM) * cdiv(N, 256);
+  if (N > 128 && tiles256 >= cx.sm_count / 2) {
     CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 256);
-    launch<256, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 256));
-  } else {
+    launch<256, MODE_GENERIC>(cx, tA, tB, p, tiles256);
+  } else if (N > 64 && cdiv(M, BM) * cdiv(N, 128) >= cx.sm_count / 2) {
     CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 128);
     launch<128, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 128));
+  } else {
+    CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 64);
+    launch<64, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 64));
   }
   return true;
 }
@@ -608,7 +599,7 @@ bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t
     attr_set = true;
   }
   dim3 grid(tiles, (unsigned)splits);
-  k_tc_atb<<<grid, NTHREADS, AtbSmem::TOTAL, cx.stream>>>(tA, tB, p);
+  k_tc_atb<<<grid, ATB_THREADS, AtbSmem::TOTAL, cx.stream>>>(tA, tB, p);
   check_launch(cx, "k_tc_atb");
   return true;
 }
@@ -626,8 +617,15 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
   if (!h_prev) h_prev = WtS_h;                                      // any valid address for the (unused) tensor map
   p.bias = bias; p.gates = gates; p.has_xproj = has_xproj; p.ptable = ptable; p.tok = tok;
   p.c_prev = c_prev; p.c_out = c_out; p.h_out = h_out; p.mask_ids = mask_ids;
-  CUtensorMap tA = make_tmap(h_prev, p.K ? R : 128, H, H, BM), tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
-  launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 64));
+  CUtensorMap tA = make_tmap(h_prev, p.K ? R : 128, H, H, BM);
+  const int tiles_big = cdiv(R, BM) * (H / 64);
+  if (tiles_big >= cx.sm_count) {            // 64 hidden units (x 4 gates = 256 columns) per tile
+    CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
+    launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
+  } else {                                   // few rows (encoder LSTMs): 16 hidden units per tile, 4x the CTAs
+    CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 16);
+    launch<64, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 16));
+  }
   return true;
 }
 
@@ -641,10 +639,18 @@ bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, con
   if (!tma_ok(Wh, 4 * H) || (da_next && !tma_ok(da_next, 4 * H))) return false;
   Params p = {};
   p.M = (int)R; p.N = H; p.K = da_next ? 4 * H : 0; p.H = H;       // K == 0: last time step, no recurrent gradient
-  if (!da_next) da_next = Wh; p.gsave = gsave; p.c_prev = c_prev; p.c_cur = c_cur; p.dh_ext = dh_ext;
+  if (!da_next) da_next = Wh;
+  p.gsave = gsave; p.c_prev = c_prev; p.c_cur = c_cur; p.dh_ext = dh_ext;
   p.dc_carry = dc_carry; p.mask_ids = mask_ids; p.da = da;
-  CUtensorMap tA = make_tmap(da_next, p.K ? R : 128, 4 * (int64_t)H, 4 * (int64_t)H, BM), tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
-  launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 128));
+  CUtensorMap tA = make_tmap(da_next, p.K ? R : 128, 4 * (int64_t)H, 4 * (int64_t)H, BM);
+  const int tiles_big = cdiv(R, BM) * (H / 128);
+  if (tiles_big >= cx.sm_count) {
+    CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
+    launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
+  } else {
+    CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 32);
+    launch<32, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
+  }
   return true;
 }
 

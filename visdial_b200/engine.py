@@ -341,6 +341,9 @@ class Engine:
         check(self.lib.vd_kernel_stats(self.h, name.encode(), C.byref(n), C.byref(ms), C.byref(fl), C.byref(by)))
         return {"launches": n.value, "ms": ms.value, "flops": fl.value, "bytes": by.value}
 
+    def profiler_range(self, start: bool):
+        check(self.lib.vd_profiler_range(self.h, int(start)))
+
     def flush_l2(self):
         check(self.lib.vd_flush_l2(self.h))
 
