@@ -167,17 +167,24 @@ def test_tf32_headline_shapes_and_rank_exactness():
     worst = max(_rel(g[s], ref["grads"][n].numpy()) for n, s in seg_slices(p).items()
                 if float(ref["grads"][n].abs().max()) > 1e-6)
     assert worst < 2e-2, worst
-    # ranks: exact wherever the oracle's gap to the neighbouring scores exceeds the TF32 noise (5e-3 abs here)
+    # Scores within the stated TF32 tolerance; ranks and argmax bit-exact wherever the oracle's gap to every other
+    # option exceeds twice the measured score deviation (inside that band a rank flip is legitimate rounding).
     ranks = eng.retrieve(Batch(nb), use_gt=False)
+    eng.set_training(0)
+    b = Batch(nb)
+    eng.encoder_forward(b)
+    got_sc = eng.decoder_forward(b).numpy()
     ev = O.forward_backward(O.Ctx(structure="batched"), p, P, tb, only_forward=True)
     sc = ev["decOut"].numpy()
+    dev = float(np.abs(got_sc - sc).max())
+    assert dev < 5e-3 * max(1.0, float(np.abs(sc).max())), dev
     ref_r = O.compute_ranks(ev["decOut"]).numpy()
     gap = np.abs(sc[:, :, None] - sc[:, None, :]) + np.eye(100)[None] * 1e9
-    safe = gap.min(2) > 5e-3                      # (N,100): options whose score is isolated
-    assert safe.mean() > 0.5
+    safe = gap.min(2) > 2 * dev                   # (N,100): options whose score is isolated
+    assert safe.mean() > 0.2, (safe.mean(), dev)
     assert np.array_equal(ranks[safe], ref_r[safe])
-    # argmax (rank-1 option) exact when the top-2 gap is safe
     srt = np.sort(sc, 1)
-    top_ok = (srt[:, -1] - srt[:, -2]) > 5e-3
+    top_ok = (srt[:, -1] - srt[:, -2]) > 2 * dev
+    assert top_ok.any()
     assert np.array_equal((ranks == 1).argmax(1)[top_ok], sc.argmax(1)[top_ok])
     eng.close()

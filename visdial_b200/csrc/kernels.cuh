@@ -109,6 +109,13 @@ void lhood_accumulate(LaunchCtx& cx, const float* logits, const int32_t* tgt, co
 void clamp_adam(LaunchCtx& cx, float* W, float* dW, float* m, float* v, int64_t n, float step, float beta1,
                 float beta2, float eps, float grad_scale);
 void fill_l2_flush(LaunchCtx& cx, float* buf, int64_t n);
+// counting sort of rows by token id (perm = row indices grouped by token, sorted_tok = their ids) and the
+// segmented row sum out[tok,:] += sum_{rows with that token} X[row,:]   (LookupTable accGradParameters in
+// projected space: the embedding gradient of the option LSTM without a 640k x 300 x 2048 contraction)
+void group_rows_by_token(LaunchCtx& cx, const int32_t* ids, int64_t n, int nv, int32_t* scratch3nv, int32_t* perm,
+                         int32_t* sorted_tok);
+void segsum_rows(LaunchCtx& cx, const float* X, int64_t ldx, const int32_t* perm, const int32_t* sorted_tok, int64_t n,
+                 float* out, int ncols);
 
 }  // namespace vd
 

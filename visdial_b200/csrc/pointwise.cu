@@ -712,6 +712,60 @@ __global__ void k_fill(float* __restrict__ buf, int64_t n, float val) {
   for (; i < n; i += stride) buf[i] = val;
 }
 
+// ---- rows grouped by token id (counting sort) + segmented row sum ---------------------------------------
+__global__ void k_tok_hist(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(counts + ids[i], 1);
+}
+// single block: offsets[v] = exclusive prefix sum of counts[v]; cursor[v] = offsets[v]
+__global__ void k_tok_scan(const int32_t* __restrict__ counts, int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int nv) {
+  __shared__ int32_t part[1024];
+  const int t = threadIdx.x, per = (nv + blockDim.x - 1) / blockDim.x;
+  const int b = t * per, e = min(nv, b + per);
+  int32_t s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) { int32_t run = 0; for (int i = 0; i < (int)blockDim.x; ++i) { int32_t v = part[i]; part[i] = run; run += v; } }
+  __syncthreads();
+  int32_t run = part[t];
+  for (int i = b; i < e; ++i) { offsets[i] = run; cursor[i] = run; run += counts[i]; }
+}
+__global__ void k_tok_fill(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
+                           int32_t* __restrict__ sorted_tok) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = ids[i];
+  int pos = atomicAdd(cursor + v, 1);
+  perm[pos] = (int32_t)i;
+  sorted_tok[pos] = v;
+}
+// Each block owns SEG_ROWS consecutive positions of the token-sorted row list; it streams those rows (ncols floats
+// each, coalesced) and flushes a running sum into out[token] whenever the token changes.  Balanced by construction.
+constexpr int SEG_ROWS = 64;
+__global__ void __launch_bounds__(256) k_segsum_rows(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ perm,
+                                                     const int32_t* __restrict__ sorted_tok, int64_t n, float* __restrict__ out,
+                                                     int ncols) {
+  const int64_t p0 = (int64_t)blockIdx.x * SEG_ROWS, p1 = min(n, p0 + SEG_ROWS);
+  for (int c0 = threadIdx.x * 4; c0 < ncols; c0 += blockDim.x * 4) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    int cur = sorted_tok[p0];
+    for (int64_t p = p0; p < p1; ++p) {
+      const int tok = sorted_tok[p];
+      if (tok != cur) {
+        float* o = out + (int64_t)cur * ncols + c0;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+        acc = make_float4(0, 0, 0, 0);
+        cur = tok;
+      }
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(X + (int64_t)perm[p] * ldx + c0));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* o = out + (int64_t)cur * ncols + c0;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+  }
+}
+
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 template <typename F>
 void set_smem(F f, size_t bytes) {
@@ -915,6 +969,23 @@ void clamp_adam(LaunchCtx& cx, float* W, float* dW, float* m, float* v, int64_t 
                 float eps, float grad_scale) {
   float omb1 = (float)(1.0 - (double)beta1), omb2 = (float)(1.0 - (double)beta2);
   L1D(k_clamp_adam, n, W, dW, m, v, n, step, beta1, beta2, omb1, omb2, eps, grad_scale);
+}
+void group_rows_by_token(LaunchCtx& cx, const int32_t* ids, int64_t n, int nv, int32_t* scratch3nv, int32_t* perm,
+                         int32_t* sorted_tok) {
+  if (n <= 0) return;
+  int32_t *counts = scratch3nv, *offsets = scratch3nv + nv, *cursor = scratch3nv + 2 * (int64_t)nv;
+  VD_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nv * sizeof(int32_t), cx.stream));
+  L1D(k_tok_hist, n, ids, n, counts);
+  k_tok_scan<<<1, 1024, 0, cx.stream>>>(counts, offsets, cursor, nv);
+  check_launch(cx, "k_tok_scan");
+  L1D(k_tok_fill, n, ids, n, cursor, perm, sorted_tok);
+}
+void segsum_rows(LaunchCtx& cx, const float* X, int64_t ldx, const int32_t* perm, const int32_t* sorted_tok, int64_t n,
+                 float* out, int ncols) {
+  if (n <= 0) return;
+  VD_REQUIRE(ncols % 4 == 0 && ldx % 4 == 0, -1, "segsum_rows: ncols, ldx must be multiples of 4");
+  k_segsum_rows<<<blocks_for(n, SEG_ROWS), 256, 0, cx.stream>>>(X, ldx, perm, sorted_tok, n, out, ncols);
+  check_launch(cx, "k_segsum_rows");
 }
 void fill_l2_flush(LaunchCtx& cx, float* buf, int64_t n) {
   k_fill<<<148 * 8, 256, 0, cx.stream>>>(buf, n, 0.f);
