@@ -145,6 +145,10 @@ Engine::Engine(const vd_params* p) {
   VD_REQUIRE(prop.major == 10, VD_E_CUDA, "visdial_b200 is built for sm_100a (B200) only");
   cx.sm_count = prop.multiProcessorCount;
   VD_CUDA_CHECK(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+  main_stream = cx.stream;
+  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+  VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   size_t bytes = (size_t)nparams * sizeof(float);
   VD_CUDA_CHECK(cudaMalloc((void**)&W, bytes));
   VD_CUDA_CHECK(cudaMalloc((void**)&dW, bytes));
@@ -184,7 +188,10 @@ Engine::~Engine() {
   for (auto e : cx.free_events) cudaEventDestroy(e);
   if (t0) cudaEventDestroy(t0);
   if (t1) cudaEventDestroy(t1);
-  cudaStreamDestroy(cx.stream);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
+  cudaStreamDestroy(main_stream);
 }
 
 int Engine::seg(const char* name) const {
@@ -417,6 +424,8 @@ static LstmRun make_run(int T, int64_t R, int D, int H, int wseg, const float* x
 
 void Engine::encoder_forward(const vd_batch* b) {
   VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  if (side_active) { cudaStreamSynchronize(side_stream); side_active = false; }   // only after an aborted call
+  cx.stream = main_stream;
   arena.reset();
   have_fwd = false;
   stage_batch(b);
@@ -438,6 +447,7 @@ void Engine::encoder_forward(const vd_batch* b) {
   const bool embdrop = cfg.enc == ENC_MN_ATT;              // mn-att-ques-im-hist.lua:24-25
   // history branch
   if (cfg.useHist) {
+    fork_side();
     xh = arena.get<float>(N * db.Th * E);
     embed_rows(cx, xh, Wp(0), ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
     hist1 = make_run(db.Th, N, E, H, seg("hist.lstm1.weight"), xh, nullptr, ids_h);
@@ -449,7 +459,9 @@ void Engine::encoder_forward(const vd_batch* b) {
     l2.x = l1.h;
     lstm_forward(l2, true);
   };
-  if (cfg.useHist) { run_two(hist1, hist2); }
+  // The history and question LSTM chains are independent until the fusion/attention stage: the history chain runs
+  // on the side stream (its tiny per-step kernels are latency-bound; overlapping the two chains hides half of it).
+  if (cfg.useHist) { fork_side(); run_two(hist1, hist2); back_to_main(); }
   // question branch
   xq = arena.get<float>(N * db.Tq * E);
   embed_rows(cx, xq, Wp(0), ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
@@ -468,6 +480,7 @@ void Engine::encoder_forward(const vd_batch* b) {
   }
   ques2 = make_run(db.Tq, N, H, H, seg("ques.lstm2.weight"), nullptr, nullptr, ids_q);
   run_two(ques1, ques2);
+  join_side();
   const float* q3 = ques2.h_last();
   const float* h3 = cfg.useHist ? hist2.h_last() : nullptr;
   encOut = arena.get<float>(N * H);
@@ -631,8 +644,18 @@ void Engine::encoder_backward(const float* dEnc) {
     add_inplace(cx, dq3, dsum1, N * H);
   }
 
-  // question LSTMs (+ gradients handed back by the gen decoder, gen.lua:45-60)
+  // question LSTMs (+ gradients handed back by the gen decoder, gen.lua:45-60); the history chain's BPTT runs
+  // concurrently on the side stream (disjoint weight segments; the shared embedding gradient is atomics-only)
   const bool embdrop = cfg.enc == ENC_MN_ATT;
+  if (cfg.useHist) {
+    fork_side();
+    float* dx2 = arena.get<float>(N * db.Th * H);
+    lstm_backward(hist2, nullptr, dh3, nullptr, dx2, nullptr, nullptr);
+    float* dx1 = arena.get<float>(N * db.Th * E);
+    lstm_backward(hist1, dx2, nullptr, nullptr, dx1, nullptr, nullptr);
+    embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
+    back_to_main();
+  }
   {
     float* dx2 = arena.get<float>(N * db.Tq * H);
     lstm_backward(ques2, nullptr, dq3, conn_dc_l2, dx2, nullptr, nullptr);
@@ -646,12 +669,24 @@ void Engine::encoder_backward(const float* dEnc) {
       linear_bwd(seg("img.embed.weight"), img_d, die, N, nullptr, 0.f);
     }
   }
-  if (cfg.useHist) {
-    float* dx2 = arena.get<float>(N * db.Th * H);
-    lstm_backward(hist2, nullptr, dh3, nullptr, dx2, nullptr, nullptr);
-    float* dx1 = arena.get<float>(N * db.Th * E);
-    lstm_backward(hist1, dx2, nullptr, nullptr, dx1, nullptr, nullptr);
-    embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
+  join_side();
+}
+
+void Engine::fork_side() {
+  if (!side_active) {
+    VD_CUDA_CHECK(cudaEventRecord(ev_fork, main_stream));
+    VD_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    side_active = true;
+  }
+  cx.stream = side_stream;
+}
+void Engine::back_to_main() { cx.stream = main_stream; }
+void Engine::join_side() {
+  cx.stream = main_stream;
+  if (side_active) {
+    VD_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
+    VD_CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev_join, 0));
+    side_active = false;
   }
 }
 

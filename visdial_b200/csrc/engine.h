@@ -90,6 +90,13 @@ struct Engine {
   float* scalars_dev = nullptr;      // [0] loss
   float* flush_buf = nullptr; int64_t flush_n = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // side stream for the independent history-LSTM chain (cx.stream is switched while its kernels are issued)
+  cudaStream_t main_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_active = false;
+  void fork_side();
+  void back_to_main();
+  void join_side();
 
   // communicator (NCCL, loaded with dlopen)
   void* nccl_comm = nullptr; int rank = 0, world = 1;

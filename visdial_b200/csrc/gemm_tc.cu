@@ -136,7 +136,7 @@ template <int BN> struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;        // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : (BN == 64) ? 8 : 10;   // small tiles are latency-bound: deeper
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
