@@ -50,18 +50,19 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The sampler runs from
+    before the warm-up; only samples whose nvidia-smi timestamp falls inside the marked window are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.t0, self.t1 = gpu_index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -71,20 +72,43 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark_begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        self.t.join(timeout=2)
+        keep = []
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                continue
+            if self.t0 is None or (self.t0 <= ts <= self.t1):
+                keep.append(r)
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = [float(r[1]) for r in keep if num(r[1])]
+        mx = [float(r[2]) for r in keep if num(r[2])]
+        pw = [float(r[3]) for r in keep if num(r[3])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in keep for i in range(4) if r[4 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
 def dist_setup(n_gpus):
@@ -217,13 +241,15 @@ def run_ours(args, rank, local, world):
         return ms, wall, eng.launch_count() - l0
 
     dev_loader, host_loader = Loader(dev_batches), Loader(host_batches)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         model.trainIteration(dev_loader)
     model.trainIteration(host_loader)
 
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark_begin()
     if args.ncu_range:                      # `ncu --profile-from-start off`: profile exactly the timed steps
         eng.profiler_range(True)
     ms_dev, wall_dev, launches = timed(dev_loader, args.steps, not args.ncu_range)
@@ -231,6 +257,8 @@ def run_ours(args, rank, local, world):
         eng.profiler_range(False)
     stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS + ("gemm", "gemm_wgrad", "allreduce")}
     ms_e2e, wall_e2e, _ = timed(host_loader, args.steps, False)
+    if rank == 0:
+        sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     ms_dev = max_over_ranks(ms_dev, world)
@@ -278,13 +306,13 @@ def run_ours(args, rank, local, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="dialogs per GPU (BASELINE config 4: 32)")
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2)
-    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ncu-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop")
     args = ap.parse_args()

@@ -1,0 +1,54 @@
+-- nn.Module-protocol objects backed by the C engine: what encoders/<name>.lua and decoders/<name>.lua return
+-- instead of an nn / nngraph module (model.lua:25-26, :42-57).  AUTHORED, NOT EXECUTED (no Lua runtime here).
+local ffi = require 'ffi'
+local vd = require 'visdial_ffi'
+
+local Half = {}
+Half.__index = Half
+
+local function newHalf(kind, params, name)
+  return setmetatable({kind = kind, params = params, name = name}, Half)
+end
+
+function Half:forward(cbatch)                       -- encoder:forward(inputs) / decoder:forward(x), model.lua:297,313,329
+  local out = ffi.new('const float*[1]')
+  if self.kind == 'enc' then vd.check(vd.C.vd_encoder_forward(self.engine, cbatch, out))
+  else vd.check(vd.C.vd_decoder_forward(self.engine, cbatch, out)) end
+  self.output = out[0]
+  return self.output
+end
+
+function Half:backward(cbatch, grad)                -- model.lua:319,323,335,337
+  if self.kind == 'enc' then
+    vd.check(vd.C.vd_encoder_backward(self.engine, cbatch, grad))
+  else
+    vd.check(vd.C.vd_decoder_backward(self.engine, cbatch))
+    local g = ffi.new('const float*[1]')
+    vd.check(vd.C.vd_backward_connect(self.engine, g))
+    return {nil, g[0]}                              -- disc: {gradOptions, gradEncOut}; the caller uses [2]
+  end
+end
+
+-- nn.Sequential():add(enc):add(dec) (model.lua:42): creates the engine = the flat parameter vector
+local Wrapper = {}
+Wrapper.__index = Wrapper
+
+function Wrapper.new(enc, dec, params)
+  local h = ffi.new('vd_engine*[1]')
+  vd.check(vd.C.vd_create(vd.params(params), h))
+  local self = setmetatable({engine = ffi.gc(h[0], vd.C.vd_destroy), enc = enc, dec = dec}, Wrapper)
+  enc.engine, dec.engine = self.engine, self.engine
+  return self
+end
+function Wrapper:cuda() return self end             -- the engine already lives on params.gpuid
+function Wrapper:get(i) return i == 1 and self.enc or self.dec end
+function Wrapper:getParameters()                    -- model.lua:55: flat device buffers
+  local W, dW = ffi.new('float*[1]'), ffi.new('float*[1]')
+  vd.check(vd.C.vd_param_buffers(self.engine, W, dW))
+  return W[0], dW[0]
+end
+function Wrapper:training() vd.check(vd.C.vd_set_training(self.engine, 1)) end
+function Wrapper:evaluate() vd.check(vd.C.vd_set_training(self.engine, 0)) end
+function Wrapper:zeroGradParameters() vd.check(vd.C.vd_zero_grad(self.engine)) end
+
+return {newHalf = newHalf, Wrapper = Wrapper}
