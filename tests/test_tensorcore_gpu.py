@@ -188,3 +188,26 @@ def test_tf32_headline_shapes_and_rank_exactness():
     assert top_ok.any()
     assert np.array_equal((ranks == 1).argmax(1)[top_ok], sc.argmax(1)[top_ok])
     eng.close()
+
+
+def test_tf32_cta_pair_kernels_match_oracle():
+    """B=4 dialogs -> 4000 option sequences: enough 128x256 tiles for the persistent cta_group::2 (CTA-pair) kernels
+    of the option LSTM to be the ones that run, forward and backward."""
+    p = full_params("mn-att-ques-im-hist", "disc")
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 4, seed=9)
+    eng = Engine(p)
+    eng.set_math_mode(VD_MATH_TF32)
+    eng.set_parameters(flat)
+    eng.set_training(1)
+    eng.set_dropout_seed(11, 3)
+    eng.zero_grad()
+    loss = eng.forward_backward(Batch(nb))
+    g = eng.get_gradients()
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3), structure="batched"), p,
+                             torch_params(p, flat), torch_batch(nb))
+    assert abs(loss - ref["loss"]) < 5e-3 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
+    for name in ("opt.lstm.weight", "opt.lstm.bias", "wordEmbed.weight", "ques.lstm1.weight", "san.out.weight"):
+        s = seg_slices(p)[name]
+        assert _rel(g[s], ref["grads"][name].numpy()) < 2e-2, name
+    eng.close()

@@ -91,6 +91,40 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: two SMs of one TPC share one 256-row MMA; each CTA stages its 128 rows
+// of A and its half of B, the leader (cluster rank 0) issues the MMAs, completion is multicast to both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
@@ -132,21 +166,26 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
   __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
 
-template <int BN> struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 4;        // 16 KB
-  static constexpr int B_BYTES = BN * BK * 4;
+template <int BN, int CG = 1> struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 4;        // 16 KB (this CTA's 128 rows)
+  static constexpr int B_BYTES = (BN / CG) * BK * 4; // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : (BN == 64) ? 8 : 10;   // small tiles are latency-bound: deeper
+  static constexpr int STAGES = (B_BYTES == 32768) ? 4 : (B_BYTES == 16384) ? 6 : (B_BYTES == 8192) ? 8 : 10;   // small tiles are latency-bound: deeper
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CG>;
   constexpr int STAGES = L::STAGES;
+  constexpr int TM = BM * CG;                        // rows per tile: 128, or 256 for a CTA pair
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int cta = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-loop index of this CTA (pair)
+  const int ncta = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + STAGES * L::STAGE_BYTES);
@@ -156,17 +195,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM;
+  const int num_m = (p.M + TM - 1) / TM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  if (CG == 2) cluster_sync_all();                  // peer barriers exist before anyone signals them
+  if (warp == 1) { if (CG == 2) tmem_alloc_cg2(tmem_slot, L::TMEM_COLS); else tmem_alloc(tmem_slot, L::TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -174,35 +214,52 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer (every CTA stages its own rows of A and its share of B) =====
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
+      for (int tile = cta; tile < num_tiles; tile += ncta) {
+        const int m0 = (tile / num_n) * TM + (int)rank * BM;
         const int nt = tile % num_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full[s], L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
-          if (MODE == MODE_LSTM_FWD) {
-            // interleave the 4 gate blocks of this hidden-unit slice: tile columns = [i | f | o | g]
-            constexpr int HB = BN / 4;
+          if (CG == 1) {
+            mbar_expect_tx(&full[s], L::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+            if (MODE == MODE_LSTM_FWD) {
+              // interleave the 4 gate blocks of this hidden-unit slice: tile columns = [i | f | o | g]
+              constexpr int HB = BN / 4;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) tma_load_2d(sb + g * HB * BK * 4, &tmB, &full[s], kb * BK, g * p.H + nt * HB);
+              for (int g = 0; g < 4; ++g) tma_load_2d(sb + g * HB * BK * 4, &tmB, &full[s], kb * BK, g * p.H + nt * HB);
+            } else {
+              tma_load_2d(sb, &tmB, &full[s], kb * BK, nt * BN);
+            }
           } else {
-            tma_load_2d(sb, &tmB, &full[s], kb * BK, nt * BN);
+            // all transactions of the pair complete on the LEADER's full barrier
+            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+            if (leader) mbar_expect_tx(&full[s], 2 * L::STAGE_BYTES);
+            tma_load_2d_cg2(sa, &tmA, bar, kb * BK, m0);
+            if (MODE == MODE_LSTM_FWD) {
+              constexpr int HB = BN / 4;              // leader stages gate blocks [i | f], peer [o | g]
+#pragma unroll
+              for (int g = 0; g < 2; ++g)
+                tma_load_2d_cg2(sb + g * HB * BK * 4, &tmB, bar, kb * BK, ((int)rank * 2 + g) * p.H + nt * HB);
+            } else {
+              tma_load_2d_cg2(sb, &tmB, bar, kb * BK, nt * BN + (int)rank * (BN / 2));
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
+  } else if (warp == 1 && !leader) {
+    // peer CTA of a pair: its MMA warp only takes part in TMEM alloc / dealloc
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc(TM, BN, 0, 0);
     int s = 0; uint32_t ph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < num_tiles; tile += ncta, ++it) {
       const int buf = it & 1;
       const uint32_t bph = (it >> 1) & 1;
       mbar_wait(&tempty[buf], bph ^ 1);
@@ -217,16 +274,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t adesc = make_desc(sa, 16, 1024);
           const uint64_t bdesc = make_desc(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(d_tmem, adesc + (uint64_t)(k * UMMA_K * 4 >> 4), bdesc + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
-                      (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);
-          if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = adesc + (uint64_t)(k * UMMA_K * 4 >> 4), bd = bdesc + (uint64_t)(k * UMMA_K * 4 >> 4);
+            if (CG == 2) umma_tf32_cg2(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            else umma_tf32(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+          if (CG == 2) { umma_commit_cg2(&empty[s]); if (kb == num_kb - 1) umma_commit_cg2(&tfull[buf]); }
+          else { umma_commit(&empty[s]); if (kb == num_kb - 1) umma_commit(&tfull[buf]); }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      if (num_kb == 0 && lane == 0) mbar_arrive(&tfull[buf]);     // K == 0: nothing to wait for, release the epilogue
+      if (num_kb == 0 && lane == 0) {                 // K == 0: nothing to wait for, release the epilogue(s)
+        mbar_arrive(&tfull[buf]);
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tfull[buf]), 1));
+      }
       __syncwarp();
     }
   } else {
@@ -234,10 +296,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < num_tiles; tile += ncta, ++it) {
       const int buf = it & 1;
       const uint32_t bph = (it >> 1) & 1;
-      const int m0 = (tile / num_n) * BM;
+      const int m0 = (tile / num_n) * TM + (int)rank * BM;
       const int nt = tile % num_n;
       mbar_wait(&tfull[buf], bph);
       tc_fence_after();
@@ -373,12 +435,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) {                                // the accumulator buffer may be overwritten by the (leader's) MMAs
+        if (CG == 2 && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
+        else mbar_arrive(&tempty[buf]);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody tears down while the peer still signals / reads
+  if (warp == 1) {
+    tc_fence_after();
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, L::TMEM_COLS); else tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -542,17 +610,37 @@ static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int6
 
 static bool tma_ok(const float* p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CG = 1>
 static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, const Params& p, int num_tiles) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  int grid = std::min(num_tiles, cx.sm_count);
-  k_tc_gemm<BN, MODE><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, p);
+  if (CG == 1) {
+    int grid = std::min(num_tiles, cx.sm_count);
+    k_tc_gemm<BN, MODE, 1><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, p);
+  } else {
+    // CTA pairs: a 2-CTA cluster per 256-row tile, one pair per TPC (num_tiles counts 256-row tiles here)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(num_tiles, cx.sm_count / 2));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = cx.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    VD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, MODE, 2>, tA, tB, p));
+  }
   check_launch(cx, "k_tc_gemm");
+}
+
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VD_CTA_PAIRS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 }  // namespace tc
@@ -621,7 +709,8 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
   const int tiles_big = cdiv(R, BM) * (H / 64);
   if (tiles_big >= cx.sm_count) {            // 64 hidden units (x 4 gates = 256 columns) per tile
     CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
-    launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
+    if (use_cta_pairs() && p.K > 0) launch<256, MODE_LSTM_FWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 64));
+    else launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
   } else {                                   // few rows (encoder LSTMs): 16 hidden units per tile, 4x the CTAs
     CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 16);
     launch<64, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 16));
@@ -646,7 +735,8 @@ bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, con
   const int tiles_big = cdiv(R, BM) * (H / 128);
   if (tiles_big >= cx.sm_count) {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
-    launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
+    if (use_cta_pairs() && p.K > 0 && H % 256 == 0) launch<256, MODE_LSTM_BWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 256));
+    else launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
   } else {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 32);
     launch<32, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
