@@ -166,20 +166,73 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
   __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
 
-template <int BN, int CG = 1> struct SmemLayout {
+// Epilogue staging (CTA-pair LSTM kernels): per epilogue warp, ARR arrays of [32 rows][16 floats].  The 16-byte
+// chunks of a row are XOR-swizzled by (row>>1)&3 so that both access patterns are bank-conflict free: "thread =
+// row" (the TMEM side) and "4 lanes = one row's 64 bytes" (the global side, coalesced 64-byte runs instead of one
+// 16-byte piece of 32 different lines per instruction, which is what saturated L1TEX before).
+constexpr int STG_ARR_BYTES = 32 * 16 * 4;
+template <int BN, int MODE, int CG> struct StageCfg {
+  static constexpr bool ON = (CG == 2 && BN == 256 && MODE != MODE_GENERIC);
+  static constexpr int ARR = !ON ? 0 : (MODE == MODE_LSTM_FWD ? 6 : 7);
+  static constexpr int BYTES = EPI_WARPS * ARR * STG_ARR_BYTES;
+};
+template <int BN, int CG = 1, int STG_BYTES = 0> struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;        // 16 KB (this CTA's 128 rows)
   static constexpr int B_BYTES = (BN / CG) * BK * 4; // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (B_BYTES == 32768) ? 4 : (B_BYTES == 16384) ? 6 : (B_BYTES == 8192) ? 8 : 10;   // small tiles are latency-bound: deeper
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int WANT = (B_BYTES == 32768) ? 4 : (B_BYTES == 16384) ? 6 : (B_BYTES == 8192) ? 8 : 10;   // small tiles are latency-bound: deeper
+  static constexpr int FIT = (232448 - 1024 - 256 - STG_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = WANT < FIT ? WANT : FIT;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
+
+__device__ __forceinline__ float4* stg_at(float* stg, int arr, int row, int q) {
+  return reinterpret_cast<float4*>(stg + (arr * 32 + row) * 16 + ((q ^ ((row >> 1) & 3)) << 2));
+}
+__device__ __forceinline__ const float* shfl_ptr(const float* p, int src_lane) {
+  unsigned long long v = (unsigned long long)p;
+  unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src_lane), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src_lane);
+  return (const float*)(((unsigned long long)hi << 32) | lo);
+}
+// global -> staging: `mine` = this lane's row base (16 floats) or nullptr (zeros); coalesced 4 lanes per row
+__device__ __forceinline__ void stg_load(float* stg, int arr, const float* mine, int lane) {
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int row = ps * 8 + (lane >> 2), q = lane & 3;
+    const float* src = shfl_ptr(mine, row);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src) v = __ldg(reinterpret_cast<const float4*>(src) + q);
+    *stg_at(stg, arr, row, q) = v;
+  }
+}
+template <bool STREAM>
+__device__ __forceinline__ void stg_store(float* stg, int arr, float* mine, int lane) {
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int row = ps * 8 + (lane >> 2), q = lane & 3;
+    float* dst = const_cast<float*>(shfl_ptr(mine, row));
+    if (dst) {
+      const float4 v = *stg_at(stg, arr, row, q);
+      if (STREAM) __stcs(reinterpret_cast<float4*>(dst) + q, v); else reinterpret_cast<float4*>(dst)[q] = v;
+    }
+  }
+}
+__device__ __forceinline__ void stg_get8(float* stg, int arr, int row, int sub, float* d) {
+  const float4 a = *stg_at(stg, arr, row, sub * 2), b = *stg_at(stg, arr, row, sub * 2 + 1);
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void stg_put8(float* stg, int arr, int row, int sub, const float* v) {
+  *stg_at(stg, arr, row, sub * 2) = make_float4(v[0], v[1], v[2], v[3]);
+  *stg_at(stg, arr, row, sub * 2 + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
 
 // ------------------------------------------------------------------------------------------------
 template <int BN, int MODE, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using L = SmemLayout<BN, CG>;
+  using SC = StageCfg<BN, MODE, CG>;
+  using L = SmemLayout<BN, CG, SC::BYTES>;
   constexpr int STAGES = L::STAGES;
   constexpr int TM = BM * CG;                        // rows per tile: 128, or 256 for a CTA pair
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
@@ -188,7 +241,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int ncta = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + STAGES * L::STAGE_BYTES);
+  float* stg_all = (float*)(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full = (uint64_t*)(smem + STAGES * L::STAGE_BYTES + SC::BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -336,6 +390,61 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
         const float* prow = (row_ok && p.ptable) ? p.ptable + (int64_t)p.tok[row] * 4 * H : nullptr;
         float* grow = p.gates ? p.gates + row * 4 * H : nullptr;
+        if constexpr (SC::ON) {
+          // staged epilogue: 16 hidden units at a time through the warp's swizzled staging tile
+          float* stg = stg_all + (warp - 2) * (SC::ARR * 32 * 16);
+#pragma unroll 1
+          for (int c = half * (HB / 2); c < (half + 1) * (HB / 2); c += 16) {
+            const int j = j0 + c;
+            // phase 1: coalesced global -> staging (x-projection rows of the 4 gates, previous cell)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float* src = nullptr;
+              if (row_ok) src = p.has_xproj ? grow + g * H + j : (prow ? prow + g * H + j : nullptr);
+              stg_load(stg, g, src, lane);
+            }
+            stg_load(stg, 4, (row_ok && p.c_prev) ? p.c_prev + row * H + j : nullptr, lane);
+            __syncwarp();
+            // phase 2: thread = row; TMEM accumulators + staged inputs -> gates, c, h back into the staging tile
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              float a[4][8], cn[8], hn[8], cp[8];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * HB + c + sub * 8, a[g]);
+              tmem_ld_wait();
+              stg_get8(stg, 4, lane, sub, cp);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float x[8], b[8];
+                stg_get8(stg, g, lane, sub, x);
+                ld8(p.bias + g * H + j + sub * 8, b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[g][e] += x[e] + b[e];
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float gi = fsigmoid(a[0][e]), gf = fsigmoid(a[1][e]), go = fsigmoid(a[2][e]), gg = ftanh(a[3][e]);
+                const float c_ = gf * cp[e] + gi * gg;
+                const float keep = masked ? 0.f : 1.f;
+                a[0][e] = gi * keep; a[1][e] = gf * keep; a[2][e] = go * keep; a[3][e] = gg * keep;
+                cn[e] = c_ * keep; hn[e] = go * ftanh(c_) * keep;
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) stg_put8(stg, g, lane, sub, a[g]);
+              stg_put8(stg, 4, lane, sub, cn);
+              stg_put8(stg, 5, lane, sub, hn);
+            }
+            __syncwarp();
+            // phase 3: staging -> global, 64-byte runs (saved gates stream past L2)
+            if (p.gates) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) stg_store<true>(stg, g, row_ok ? grow + g * H + j : nullptr, lane);
+            }
+            stg_store<false>(stg, 4, row_ok ? p.c_out + row * H + j : nullptr, lane);
+            stg_store<false>(stg, 5, row_ok ? p.h_out + row * H + j : nullptr, lane);
+            __syncwarp();
+          }
+        } else {
 #pragma unroll 1
         for (int c = half * (HB / 2); c < (half + 1) * (HB / 2); c += 8) {
           const int j = j0 + c;
@@ -382,9 +491,62 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           __syncwarp();
         }
+        }   // !SC::ON
       } else {   // MODE_LSTM_BWD: accumulator = dh_rec for hidden units [nt*BN, nt*BN + BN)
         const int H = p.H, j0 = nt * BN;
         const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
+        if constexpr (SC::ON) {
+          float* stg = stg_all + (warp - 2) * (SC::ARR * 32 * 16);
+#pragma unroll 1
+          for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+            const int j = j0 + c;
+            // phase 1: saved gates (4), c_prev, c_t, dc carry -> staging, coalesced
+#pragma unroll
+            for (int g = 0; g < 4; ++g) stg_load(stg, g, row_ok ? p.gsave + row * 4 * H + g * H + j : nullptr, lane);
+            stg_load(stg, 4, (row_ok && p.c_prev) ? p.c_prev + row * H + j : nullptr, lane);
+            stg_load(stg, 5, row_ok ? p.c_cur + row * H + j : nullptr, lane);
+            stg_load(stg, 6, row_ok ? p.dc_carry + row * H + j : nullptr, lane);
+            __syncwarp();
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              float dh[8], g[4][8], cp[8], cc[8], dc[8], out[4][8], dcn[8];
+              tmem_ld8(taddr + c + sub * 8, dh);
+              tmem_ld_wait();
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) stg_get8(stg, gg, lane, sub, g[gg]);
+              stg_get8(stg, 4, lane, sub, cp);
+              stg_get8(stg, 5, lane, sub, cc);
+              stg_get8(stg, 6, lane, sub, dc);
+              if (p.dh_ext && row_ok) {          // only the last time step has an external gradient here
+                float ex[8];
+                ld8(p.dh_ext + row * H + j + sub * 8, ex);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dh[e] += ex[e];
+              }
+              const float keep = masked ? 0.f : 1.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
+                const float tcv = ftanh(cc[e]);
+                const float d = (dc[e] + dh[e] * go * (1.f - tcv * tcv)) * keep;
+                const float dhe = dh[e] * keep;
+                out[0][e] = d * gg_ * gi * (1.f - gi);
+                out[1][e] = d * cp[e] * gf * (1.f - gf);
+                out[2][e] = dhe * tcv * go * (1.f - go);
+                out[3][e] = d * gi * (1.f - gg_ * gg_);
+                dcn[e] = d * gf;
+              }
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) stg_put8(stg, gg, lane, sub, out[gg]);
+              stg_put8(stg, 6, lane, sub, dcn);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) stg_store<false>(stg, gg, row_ok ? p.da + row * 4 * H + gg * H + j : nullptr, lane);
+            stg_store<false>(stg, 6, row_ok ? p.dc_carry + row * H + j : nullptr, lane);
+            __syncwarp();
+          }
+        } else {
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
           const int j = j0 + c;
@@ -432,6 +594,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           __syncwarp();
         }
+        }   // !SC::ON
       }
       tc_fence_before();
       __syncwarp();
@@ -612,7 +775,7 @@ static bool tma_ok(const float* p, int64_t ld) { return ((uintptr_t)p % 16 == 0)
 
 template <int BN, int MODE, int CG = 1>
 static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, const Params& p, int num_tiles) {
-  using L = SmemLayout<BN, CG>;
+  using L = SmemLayout<BN, CG, StageCfg<BN, MODE, CG>::BYTES>;
   static bool attr_set = false;
   if (!attr_set) {
     VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
