@@ -291,16 +291,19 @@ void Engine::lstm_forward(LstmRun& r, bool save) {
   // kernel: recurrent tcgen05 GEMM + SeqLSTM pointwise epilogue.
   const bool tc = math_mode == VD_MATH_TF32 && H % 64 == 0;
   const float* ptable = nullptr;
+  // on the tensor-core path the bias is folded into the x-projection (table or batched GEMM epilogue), so the
+  // per-step kernel reads one array less
+  const float* xbias = tc ? bias : nullptr;
   if (tc && r.gather) {
     float* pt = arena.get<float>((int64_t)(cfg.V + 1) * G);
-    gemm_tn(cfg.V + 1, G, D, Wp(0), cfg.E, nullptr, WtS, D + H, pt, G, 0.f, nullptr, 0);
+    gemm_tn(cfg.V + 1, G, D, Wp(0), cfg.E, nullptr, WtS, D + H, pt, G, 0.f, xbias, 0);
     ptable = pt;
   }
   if (save) {
     r.h = arena.get<float>((int64_t)r.T * R * H);
     r.c = arena.get<float>((int64_t)r.T * R * H);
     r.gates = arena.get<float>((int64_t)r.T * R * G);
-    if (!ptable) gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, nullptr, 0);
+    if (!ptable) gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, xbias, 0);
   } else {
     r.h = arena.get<float>(2 * R * H);
     r.c = arena.get<float>(2 * R * H);
@@ -318,11 +321,11 @@ void Engine::lstm_forward(LstmRun& r, bool save) {
       if (!ptable) {
         if (!save) {
           const float* At = r.x + (int64_t)t * R * D;
-          gemm_tn((int)R, G, D, At, lda, nullptr, WtS, D + H, g, G, 0.f, nullptr, 0);
+          gemm_tn((int)R, G, D, At, lda, nullptr, WtS, D + H, g, G, 0.f, xbias, 0);
         }
         has_x = 1;
       }
-      if (lstm_step_fwd_tc(cx, R, H, hp, WtS + D, D + H, bias, (save || has_x) ? g : nullptr, has_x, ptable,
+      if (lstm_step_fwd_tc(cx, R, H, hp, WtS + D, D + H, nullptr, (save || has_x) ? g : nullptr, has_x, ptable,
                            ptable ? r.gather + (int64_t)t * R : nullptr, cp, r.c + slot * R * H, r.h + slot * R * H, mk))
         continue;
       VD_REQUIRE(false, VD_E_STATE, "lstm_step_fwd_tc refused a shape the engine routed to it");

@@ -101,7 +101,9 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the arrive only has to follow the TMEM reads (ordered by tcgen05.fence::before_thread_sync); a release
+  // at cluster scope compiles to MEMBAR.ALL.GPU and would wait for the epilogue's global stores to drain.
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(
@@ -415,11 +417,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               stg_get8(stg, 4, lane, sub, cp);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                float x[8], b[8];
+                float x[8];
                 stg_get8(stg, g, lane, sub, x);
-                ld8(p.bias + g * H + j + sub * 8, b);
+                if (p.bias) add8(p.bias + g * H + j + sub * 8, x);     // null when folded into the x-projection
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[g][e] += x[e] + b[e];
+                for (int e = 0; e < 8; ++e) a[g][e] += x[e];
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -453,7 +455,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (row_ok && !masked) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              ld8(p.bias + g * H + j, x[g]);
+              if (p.bias) ld8(p.bias + g * H + j, x[g]);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[g][e] = 0.f;
+              }
               if (p.has_xproj) add8(grow + g * H + j, x[g]);
               if (prow) add8(prow + g * H + j, x[g]);
             }
