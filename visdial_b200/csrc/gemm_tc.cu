@@ -174,7 +174,7 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
 // 16-byte piece of 32 different lines per instruction, which is what saturated L1TEX before).
 constexpr int STG_ARR_BYTES = 32 * 16 * 4;
 template <int BN, int MODE, int CG> struct StageCfg {
-  static constexpr bool ON = (CG == 2 && BN == 256 && MODE != MODE_GENERIC);
+  static constexpr bool ON = (CG == 2 && MODE != MODE_GENERIC && (BN == 256 || (BN == 128 && MODE == MODE_LSTM_BWD)));
   static constexpr int ARR = !ON ? 0 : (MODE == MODE_LSTM_FWD ? 6 : 7);
   static constexpr int BYTES = EPI_WARPS * ARR * STG_ARR_BYTES;
 };
@@ -197,16 +197,22 @@ __device__ __forceinline__ const float* shfl_ptr(const float* p, int src_lane) {
   unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src_lane), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src_lane);
   return (const float*)(((unsigned long long)hi << 32) | lo);
 }
-// global -> staging: `mine` = this lane's row base (16 floats) or nullptr (zeros); coalesced 4 lanes per row
+// global -> staging: `mine` = this lane's row base (16 floats) or nullptr (zeros); coalesced 4 lanes per row.
+// cp.async (LDGSTS): no register staging, so every array of a group is in flight at once and the global latency is
+// paid once per group instead of once per array; the caller ends the group with stg_load_wait().
 __device__ __forceinline__ void stg_load(float* stg, int arr, const float* mine, int lane) {
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int row = ps * 8 + (lane >> 2), q = lane & 3;
     const float* src = shfl_ptr(mine, row);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (src) v = __ldg(reinterpret_cast<const float4*>(src) + q);
-    *stg_at(stg, arr, row, q) = v;
+    float4* dst = stg_at(stg, arr, row, q);
+    if (src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + q * 4) : "memory");
+    else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+__device__ __forceinline__ void stg_load_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 }
 template <bool STREAM>
 __device__ __forceinline__ void stg_store(float* stg, int arr, float* mine, int lane) {
@@ -406,7 +412,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               stg_load(stg, g, src, lane);
             }
             stg_load(stg, 4, (row_ok && p.c_prev) ? p.c_prev + row * H + j : nullptr, lane);
-            __syncwarp();
+            stg_load_wait();
             // phase 2: thread = row; TMEM accumulators + staged inputs -> gates, c, h back into the staging tile
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
@@ -512,7 +518,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             stg_load(stg, 4, (row_ok && p.c_prev) ? p.c_prev + row * H + j : nullptr, lane);
             stg_load(stg, 5, row_ok ? p.c_cur + row * H + j : nullptr, lane);
             stg_load(stg, 6, row_ok ? p.dc_carry + row * H + j : nullptr, lane);
-            __syncwarp();
+            stg_load_wait();
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
               float dh[8], g[4][8], cp[8], cc[8], dc[8], out[4][8], dcn[8];
@@ -904,8 +910,16 @@ bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, con
   const int tiles_big = cdiv(R, BM) * (H / 128);
   if (tiles_big >= cx.sm_count) {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
-    if (use_cta_pairs() && p.K > 0 && H % 256 == 0) launch<256, MODE_LSTM_BWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 256));
-    else launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
+    static int bwd_bn = -1;
+    if (bwd_bn < 0) { const char* e = getenv("VD_BWD_BN"); bwd_bn = (e && atoi(e) == 256) ? 256 : 128; }
+    if (use_cta_pairs() && p.K > 0 && bwd_bn == 256 && H % 256 == 0) {
+      launch<256, MODE_LSTM_BWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 256));
+    } else if (use_cta_pairs() && p.K > 0) {
+      // 128 hidden units per pair-tile: twice the tiles of the 256-wide variant -> a fuller last wave (250 vs 500
+      // tiles over 74 CTA pairs)
+      CUtensorMap tB64 = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 64);
+      launch<128, MODE_LSTM_BWD, 2>(cx, tA, tB64, p, cdiv(R, 2 * BM) * (H / 128));
+    } else launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
   } else {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 32);
     launch<32, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
