@@ -210,6 +210,16 @@ __device__ __forceinline__ void stg_load(float* stg, int arr, const float* mine,
     else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
+// staging -> global through the TMA (one bulk tensor store per array instead of 4 passes of shuffles + LDS + STG per
+// lane): the staging arrays are laid out exactly like a SWIZZLE_64B box of 32 rows x 16 floats.
+struct EpiMaps { CUtensorMap g4, c, h; };      // [R,4H] gates / da;  [R,H] c_out / dc_carry;  [R,H] h_out
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void stg_load_wait() {
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();
@@ -238,7 +248,8 @@ __device__ __forceinline__ void stg_put8(float* stg, int arr, int row, int sub, 
 // ------------------------------------------------------------------------------------------------
 template <int BN, int MODE, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ EpiMaps em, const Params p) {
   using SC = StageCfg<BN, MODE, CG>;
   using L = SmemLayout<BN, CG, SC::BYTES>;
   constexpr int STAGES = L::STAGES;
@@ -404,6 +415,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll 1
           for (int c = half * (HB / 2); c < (half + 1) * (HB / 2); c += 16) {
             const int j = j0 + c;
+            if (lane == 0) bulk_wait_read0();    // the previous group's TMA stores have finished reading the staging tile
+            __syncwarp();
             // phase 1: coalesced global -> staging (x-projection rows of the 4 gates, previous cell)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -442,14 +455,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               stg_put8(stg, 4, lane, sub, cn);
               stg_put8(stg, 5, lane, sub, hn);
             }
+            // phase 3: staging -> global by TMA tensor stores (rows beyond R are clipped by the tensor map)
+            fence_proxy_async_smem();
             __syncwarp();
-            // phase 3: staging -> global, 64-byte runs (saved gates stream past L2)
-            if (p.gates) {
+            if (lane == 0) {
+              const int r0 = m0 + q * 32;
+              if (p.gates) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) stg_store<true>(stg, g, row_ok ? grow + g * H + j : nullptr, lane);
+                for (int g = 0; g < 4; ++g) tma_store_2d(&em.g4, stg + g * 512, g * H + j, r0);
+              }
+              tma_store_2d(&em.c, stg + 4 * 512, j, r0);
+              tma_store_2d(&em.h, stg + 5 * 512, j, r0);
+              bulk_commit();
             }
-            stg_store<false>(stg, 4, row_ok ? p.c_out + row * H + j : nullptr, lane);
-            stg_store<false>(stg, 5, row_ok ? p.h_out + row * H + j : nullptr, lane);
             __syncwarp();
           }
         } else {
@@ -512,6 +530,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll 1
           for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
             const int j = j0 + c;
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
             // phase 1: saved gates (4), c_prev, c_t, dc carry -> staging, coalesced
 #pragma unroll
             for (int g = 0; g < 4; ++g) stg_load(stg, g, row_ok ? p.gsave + row * 4 * H + g * H + j : nullptr, lane);
@@ -552,10 +572,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               for (int gg = 0; gg < 4; ++gg) stg_put8(stg, gg, lane, sub, out[gg]);
               stg_put8(stg, 6, lane, sub, dcn);
             }
+            fence_proxy_async_smem();
             __syncwarp();
+            if (lane == 0) {
+              const int r0 = m0 + q * 32;
 #pragma unroll
-            for (int gg = 0; gg < 4; ++gg) stg_store<false>(stg, gg, row_ok ? p.da + row * 4 * H + gg * H + j : nullptr, lane);
-            stg_store<false>(stg, 6, row_ok ? p.dc_carry + row * H + j : nullptr, lane);
+              for (int gg = 0; gg < 4; ++gg) tma_store_2d(&em.g4, stg + gg * 512, gg * H + j, r0);
+              tma_store_2d(&em.c, stg + 6 * 512, j, r0);
+              bulk_commit();
+            }
             __syncwarp();
           }
         } else {
@@ -615,6 +640,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         else mbar_arrive(&tempty[buf]);
       }
     }
+    if (SC::ON && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores performed
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody tears down while the peer still signals / reads
@@ -786,8 +812,11 @@ static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int6
 static bool tma_ok(const float* p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
 
 template <int BN, int MODE, int CG = 1>
-static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, const Params& p, int num_tiles) {
+static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, const Params& p, int num_tiles,
+                   const EpiMaps* epi = nullptr) {
   using L = SmemLayout<BN, CG, StageCfg<BN, MODE, CG>::BYTES>;
+  static EpiMaps none = {};
+  const EpiMaps& em = epi ? *epi : none;
   static bool attr_set = false;
   if (!attr_set) {
     VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -795,7 +824,7 @@ static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, 
   }
   if (CG == 1) {
     int grid = std::min(num_tiles, cx.sm_count);
-    k_tc_gemm<BN, MODE, 1><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, p);
+    k_tc_gemm<BN, MODE, 1><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, em, p);
   } else {
     // CTA pairs: a 2-CTA cluster per 256-row tile, one pair per TPC (num_tiles counts 256-row tiles here)
     cudaLaunchConfig_t cfg = {};
@@ -807,7 +836,7 @@ static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, 
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    VD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, MODE, 2>, tA, tB, p));
+    VD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, MODE, 2>, tA, tB, em, p));
   }
   check_launch(cx, "k_tc_gemm");
 }
@@ -884,7 +913,13 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
   const int tiles_big = cdiv(R, BM) * (H / 64);
   if (tiles_big >= cx.sm_count) {            // 64 hidden units (x 4 gates = 256 columns) per tile
     CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
-    if (use_cta_pairs() && p.K > 0) launch<256, MODE_LSTM_FWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 64));
+    if (use_cta_pairs() && p.K > 0) {
+      EpiMaps em;                              // epilogue outputs leave through TMA tensor stores (64B-swizzled boxes)
+      em.g4 = make_tmap(gates ? gates : c_out, R, gates ? 4 * (int64_t)H : H, gates ? 4 * (int64_t)H : H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      em.c = make_tmap(c_out, R, H, H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      em.h = make_tmap(h_out, R, H, H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      launch<256, MODE_LSTM_FWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 64), &em);
+    }
     else launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
   } else {                                   // few rows (encoder LSTMs): 16 hidden units per tile, 4x the CTAs
     CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 16);
@@ -911,14 +946,22 @@ bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, con
   if (tiles_big >= cx.sm_count) {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
     static int bwd_bn = -1;
-    if (bwd_bn < 0) { const char* e = getenv("VD_BWD_BN"); bwd_bn = (e && atoi(e) == 256) ? 256 : 128; }
+    if (bwd_bn < 0) { const char* e = getenv("VD_BWD_BN"); bwd_bn = (e && atoi(e) == 128) ? 128 : 256; }
     if (use_cta_pairs() && p.K > 0 && bwd_bn == 256 && H % 256 == 0) {
-      launch<256, MODE_LSTM_BWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 256));
+      EpiMaps em;
+      em.g4 = make_tmap(da, R, 4 * (int64_t)H, 4 * (int64_t)H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      em.c = make_tmap(dc_carry, R, H, H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      em.h = em.c;
+      launch<256, MODE_LSTM_BWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 256), &em);
     } else if (use_cta_pairs() && p.K > 0) {
       // 128 hidden units per pair-tile: twice the tiles of the 256-wide variant -> a fuller last wave (250 vs 500
       // tiles over 74 CTA pairs)
       CUtensorMap tB64 = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 64);
-      launch<128, MODE_LSTM_BWD, 2>(cx, tA, tB64, p, cdiv(R, 2 * BM) * (H / 128));
+      EpiMaps em;
+      em.g4 = make_tmap(da, R, 4 * (int64_t)H, 4 * (int64_t)H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      em.c = make_tmap(dc_carry, R, H, H, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+      em.h = em.c;
+      launch<128, MODE_LSTM_BWD, 2>(cx, tA, tB64, p, cdiv(R, 2 * BM) * (H / 128), &em);
     } else launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
   } else {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 32);
