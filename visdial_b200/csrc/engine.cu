@@ -325,6 +325,11 @@ void Engine::lstm_forward(LstmRun& r, bool save) {
         }
         has_x = 1;
       }
+      if (!hp) {          // t = 0 without h0: no recurrent term, a plain streaming kernel (x-projection already has the bias)
+        lstm_first_step_fwd(cx, (save || has_x) ? g : nullptr, ptable, ptable ? r.gather + (int64_t)t * R : nullptr, nullptr,
+                            cp, mk, r.c + slot * R * H, r.h + slot * R * H, R, H);
+        continue;
+      }
       if (lstm_step_fwd_tc(cx, R, H, hp, WtS + D, D + H, nullptr, (save || has_x) ? g : nullptr, has_x, ptable,
                            ptable ? r.gather + (int64_t)t * R : nullptr, cp, r.c + slot * R * H, r.h + slot * R * H, mk))
         continue;
@@ -364,6 +369,11 @@ void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last
       const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
       const float* ext = (t == r.T - 1) ? ext_last : (dh_all ? dh_all + (int64_t)t * R * H : nullptr);
       LaunchCtx::Scope sc(&cx, "lstm_step_bwd", t == r.T - 1 ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
+      if (t == r.T - 1) {   // last step: no recurrent gradient yet, pointwise only
+        lstm_pointwise_bwd(cx, r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, nullptr, ext, nullptr, dc_carry,
+                           r.mask ? r.mask + (int64_t)t * R : nullptr, da + (int64_t)t * R * G, R, H);
+        continue;
+      }
       bool ok = lstm_step_bwd_tc(cx, R, H, t == r.T - 1 ? nullptr : da + (int64_t)(t + 1) * R * G, Ws + (int64_t)D * G,
                                  r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, ext, dc_carry,
                                  r.mask ? r.mask + (int64_t)t * R : nullptr, da + (int64_t)t * R * G);

@@ -174,8 +174,8 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
 // 16-byte piece of 32 different lines per instruction, which is what saturated L1TEX before).
 constexpr int STG_ARR_BYTES = 32 * 16 * 4;
 template <int BN, int MODE, int CG> struct StageCfg {
-  static constexpr bool ON = (CG == 2 && MODE != MODE_GENERIC && (BN == 256 || (BN == 128 && MODE == MODE_LSTM_BWD)));
-  static constexpr int ARR = !ON ? 0 : (MODE == MODE_LSTM_FWD ? 6 : 7);
+  static constexpr bool ON = MODE == MODE_GENERIC || (CG == 2 && (BN == 256 || (BN == 128 && MODE == MODE_LSTM_BWD)));
+  static constexpr int ARR = !ON ? 0 : (MODE == MODE_GENERIC ? 1 : MODE == MODE_LSTM_FWD ? 6 : 7);
   static constexpr int BYTES = EPI_WARPS * ARR * STG_ARR_BYTES;
 };
 template <int BN, int CG = 1, int STG_BYTES = 0> struct SmemLayout {
@@ -381,26 +381,48 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 
       if (MODE == MODE_GENERIC) {
+        // 16 output columns at a time through the warp's staging array; C leaves (and, for beta != 0, enters)
+        // as 64-byte-swizzled boxes: TMA tensor store / cp.async load.  Rows >= M and columns >= N are clipped.
         const int n0 = nt * BN;
+        float* stg = stg_all + (warp - 2) * (SC::ARR * 32 * 16);
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
           if (n0 + c >= p.N) break;                 // warp-uniform
-          float v[8];
-          tmem_ld8(taddr + c, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            float* crow = p.C + row * p.ldc + n0 + c;
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          if (p.beta != 0.f) {
+            const bool full16 = n0 + c + 16 <= p.N;
+            stg_load(stg, 0, (row_ok && full16) ? p.C + row * p.ldc + n0 + c : nullptr, lane);
+            stg_load_wait();
+            if (!full16 && row_ok) {               // ragged last group: element-wise
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int n = n0 + c + j;
-              if (n < p.N) {
-                float x = v[j];
-                if (p.bias) x += __ldg(p.bias + n);
-                if (p.beta != 0.f) x += p.beta * crow[j];
-                crow[j] = p.act == 1 ? ftanh(x) : x;
+              for (int sub = 0; sub < 2; ++sub) {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int n = n0 + c + sub * 8 + j; t[j] = n < p.N ? p.C[row * p.ldc + n] : 0.f; }
+                stg_put8(stg, 0, lane, sub, t);
               }
             }
           }
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            float v[8], old[8];
+            tmem_ld8(taddr + c + sub * 8, v);
+            tmem_ld_wait();
+            if (p.beta != 0.f) stg_get8(stg, 0, lane, sub, old);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int n = n0 + c + sub * 8 + j;
+              float x = v[j];
+              if (p.bias && n < p.N) x += __ldg(p.bias + n);
+              if (p.beta != 0.f) x += p.beta * old[j];
+              v[j] = p.act == 1 ? ftanh(x) : x;
+            }
+            stg_put8(stg, 0, lane, sub, v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&em.g4, stg, n0 + c, m0 + q * 32); bulk_commit(); }
           __syncwarp();
         }
       } else if (MODE == MODE_LSTM_FWD) {
@@ -855,19 +877,21 @@ bool gemm_tn_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda,
   using namespace tc;
   if (a_gather) return false;                               // gathered rows go through the projection table instead
   if (M < 64 || N < 16 || K < 32) return false;             // tiny contractions stay on CUDA cores
-  if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
+  if (!tma_ok(A, lda) || !tma_ok(B, ldb) || !tma_ok(C, ldc)) return false;
   Params p = {};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.beta = beta; p.bias = bias; p.act = act;
+  EpiMaps em = {};
+  em.g4 = make_tmap(C, M, N, ldc, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);      // C leaves through TMA tensor stores
   const int tiles256 = cdiv(M, BM) * cdiv(N, 256);
   if (N > 128 && tiles256 >= cx.sm_count / 2) {
     CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 256);
-    launch<256, MODE_GENERIC>(cx, tA, tB, p, tiles256);
+    launch<256, MODE_GENERIC>(cx, tA, tB, p, tiles256, &em);
   } else if (N > 64 && cdiv(M, BM) * cdiv(N, 128) >= cx.sm_count / 2) {
     CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 128);
-    launch<128, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 128));
+    launch<128, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 128), &em);
   } else {
     CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 64);
-    launch<64, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 64));
+    launch<64, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 64), &em);
   }
   return true;
 }

@@ -34,6 +34,10 @@ void embed_scatter_add(LaunchCtx& cx, float* demb, const float* dx, int64_t ldx,
 // gates (R,4H) holds pre-activations without bias on entry, activated [i f o g] on exit.
 void lstm_pointwise_fwd(LaunchCtx& cx, float* gates, const float* bias, const float* c_prev,
                         const int32_t* mask_ids, float* c_out, float* h_out, int64_t R, int H);
+// first step of a sequence without initial state: no recurrent term, the pre-activation is the x-projection
+// (in `gates`, or gathered from `ptable[tok]`), bias optional
+void lstm_first_step_fwd(LaunchCtx& cx, float* gates, const float* ptable, const int32_t* tok, const float* bias,
+                         const float* c_prev, const int32_t* mask_ids, float* c_out, float* h_out, int64_t R, int H);
 // da (R,4H) out; dc_carry (R,H) in: dc from step t+1, out: dc for step t-1.
 void lstm_pointwise_bwd(LaunchCtx& cx, const float* gates, const float* c_prev, const float* c,
                         const float* dh_rec, const float* dh_ext, const float* dc_ext, float* dc_carry,

@@ -139,6 +139,46 @@ __global__ void k_lstm_pw_fwd(float* __restrict__ gates, const float* __restrict
   reinterpret_cast<float4*>(h_out + r * H)[j >> 2] = hn;
 }
 
+// SeqLSTM step with no recurrent term (t = 0 without h0): pre-activation = x-projection (+ bias), taken either from
+// the gates buffer (in place) or gathered from the projection table.  One thread per (row, 4 hidden units).
+__global__ void k_lstm_first_step(float* __restrict__ gates, const float* __restrict__ ptable, const int32_t* __restrict__ tok,
+                                  const float* __restrict__ bias, const float* __restrict__ c_prev,
+                                  const int32_t* __restrict__ mask_ids, float* __restrict__ c_out, float* __restrict__ h_out,
+                                  int64_t R, int H) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int H4 = H >> 2;
+  if (idx >= R * H4) return;
+  const int64_t r = idx / H4;
+  const int j = (int)(idx % H4) * 4;
+  const float4 zero = make_float4(0, 0, 0, 0);
+  const bool masked = mask_ids && mask_ids[r] == 0;
+  const float* src = ptable ? ptable + (int64_t)tok[r] * 4 * H : gates + r * 4 * H;
+  float4 a[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    a[g] = *reinterpret_cast<const float4*>(src + g * H + j);
+    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + g * H + j); a[g].x += b.x; a[g].y += b.y; a[g].z += b.z; a[g].w += b.w; }
+  }
+  const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + r * H + j) : zero;
+  float4 cn, hn;
+  float* pa[4] = {&a[0].x, &a[1].x, &a[2].x, &a[3].x};
+  const float* pc = &cp.x; float* pcn = &cn.x; float* phn = &hn.x;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float gi = sigmoidf_(pa[0][q]), gf = sigmoidf_(pa[1][q]), go = sigmoidf_(pa[2][q]), gg = tanhf(pa[3][q]);
+    float c = gf * pc[q] + gi * gg;
+    float keep = masked ? 0.f : 1.f;
+    pa[0][q] = gi * keep; pa[1][q] = gf * keep; pa[2][q] = go * keep; pa[3][q] = gg * keep;
+    pcn[q] = c * keep; phn[q] = go * tanhf(c) * keep;
+  }
+  if (gates) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(gates + r * 4 * H + g * H + j) = a[g];
+  }
+  *reinterpret_cast<float4*>(c_out + r * H + j) = cn;
+  *reinterpret_cast<float4*>(h_out + r * H + j) = hn;
+}
+
 __global__ void k_lstm_pw_bwd(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c,
                               const float* __restrict__ dh_rec, const float* __restrict__ dh_ext,
                               const float* __restrict__ dc_ext, float* __restrict__ dc_carry,
@@ -799,6 +839,11 @@ void lstm_pointwise_fwd(LaunchCtx& cx, float* gates, const float* bias, const fl
                         float* c_out, float* h_out, int64_t R, int H) {
   VD_REQUIRE(H % 4 == 0, -1, "rnnHiddenSize must be a multiple of 4");
   L1D(k_lstm_pw_fwd, R * (H / 4), gates, bias, c_prev, mask_ids, c_out, h_out, R, H);
+}
+void lstm_first_step_fwd(LaunchCtx& cx, float* gates, const float* ptable, const int32_t* tok, const float* bias,
+                         const float* c_prev, const int32_t* mask_ids, float* c_out, float* h_out, int64_t R, int H) {
+  VD_REQUIRE(H % 4 == 0 && (gates || ptable), -1, "lstm_first_step_fwd: bad arguments");
+  L1D(k_lstm_first_step, R * (H / 4), gates, ptable, tok, bias, c_prev, mask_ids, c_out, h_out, R, H);
 }
 void lstm_pointwise_bwd(LaunchCtx& cx, const float* gates, const float* c_prev, const float* c, const float* dh_rec,
                         const float* dh_ext, const float* dc_ext, float* dc_carry, const int32_t* mask_ids, float* da,
