@@ -147,6 +147,8 @@ Engine::Engine(const vd_params* p) {
   VD_CUDA_CHECK(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
   main_stream = cx.stream;
   VD_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&main2_stream, cudaStreamNonBlocking));
+  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&side2_stream, cudaStreamNonBlocking));
   VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   size_t bytes = (size_t)nparams * sizeof(float);
@@ -191,6 +193,9 @@ Engine::~Engine() {
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
   if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
+  if (main2_stream) { cudaStreamSynchronize(main2_stream); cudaStreamDestroy(main2_stream); }
+  if (side2_stream) { cudaStreamSynchronize(side2_stream); cudaStreamDestroy(side2_stream); }
+  for (auto e : ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(main_stream);
 }
 
@@ -275,7 +280,7 @@ void Engine::stage_batch(const vd_batch* b) {
 // nn.SeqLSTM [upstream rnn], SURVEY.md Appendix C.  Forward: one batched x-projection (or per step in
 // the non-saving mode) + per step {recurrent GEMM, pointwise}.
 // ------------------------------------------------------------------------------------------------
-void Engine::lstm_forward(LstmRun& r, bool save) {
+void Engine::lstm_forward_begin(LstmRun& r, bool save) {
   const Seg& ws = lay.segs[r.wseg];
   VD_REQUIRE(ws.rows == r.D + r.H && ws.cols == 4 * r.H, VD_E_STATE, "lstm weight shape");
   const int H = r.H, D = r.D, G = 4 * r.H;
@@ -289,110 +294,167 @@ void Engine::lstm_forward(LstmRun& r, bool save) {
   // computed once per forward (E Wx^T: the 300-wide half of every step's contraction collapses into a
   // gather in the step epilogue); a dense input keeps the batched x-projection.  Each step is then ONE fused
   // kernel: recurrent tcgen05 GEMM + SeqLSTM pointwise epilogue.
-  const bool tc = math_mode == VD_MATH_TF32 && H % 64 == 0;
-  const float* ptable = nullptr;
-  // on the tensor-core path the bias is folded into the x-projection (table or batched GEMM epilogue), so the
-  // per-step kernel reads one array less
-  const float* xbias = tc ? bias : nullptr;
-  if (tc && r.gather) {
+  r.tc = math_mode == VD_MATH_TF32 && H % 64 == 0;
+  r.ptable = nullptr;
+  // on the tensor-core path the bias is folded into the x-projection (table or GEMM epilogue), so the per-step
+  // kernel reads one array less
+  const float* xbias = r.tc ? bias : nullptr;
+  if (r.tc && r.gather) {
     float* pt = arena.get<float>((int64_t)(cfg.V + 1) * G);
     gemm_tn(cfg.V + 1, G, D, Wp(0), cfg.E, nullptr, WtS, D + H, pt, G, 0.f, xbias, 0);
-    ptable = pt;
+    r.ptable = pt;
   }
   if (save) {
     r.h = arena.get<float>((int64_t)r.T * R * H);
     r.c = arena.get<float>((int64_t)r.T * R * H);
     r.gates = arena.get<float>((int64_t)r.T * R * G);
-    if (!ptable) gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, xbias, 0);
+    if (!r.ptable && !(r.tc && r.step_xproj))
+      gemm_tn((int)((int64_t)r.T * R), G, D, A, lda, r.gather, WtS, D + H, r.gates, G, 0.f, xbias, 0);
   } else {
     r.h = arena.get<float>(2 * R * H);
     r.c = arena.get<float>(2 * R * H);
     r.gates = arena.get<float>(R * G);
   }
-  for (int t = 0; t < r.T; ++t) {
-    const int64_t slot = save ? t : (t & 1), pslot = save ? t - 1 : ((t - 1) & 1);
-    float* g = save ? r.gates + (int64_t)t * R * G : r.gates;
-    const float* hp = t > 0 ? r.h + pslot * R * H : r.h0;
-    const float* cp = t > 0 ? r.c + pslot * R * H : r.c0;
-    LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * (H + ((save && !ptable) ? 0 : D)), 4.0 * R * (G + 4.0 * H));
-    if (tc) {
-      const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
-      int has_x = 0;
-      if (!ptable) {
-        if (!save) {
-          const float* At = r.x + (int64_t)t * R * D;
-          gemm_tn((int)R, G, D, At, lda, nullptr, WtS, D + H, g, G, 0.f, xbias, 0);
-        }
-        has_x = 1;
-      }
-      if (!hp) {          // t = 0 without h0: no recurrent term, a plain streaming kernel (x-projection already has the bias)
-        lstm_first_step_fwd(cx, (save || has_x) ? g : nullptr, ptable, ptable ? r.gather + (int64_t)t * R : nullptr, nullptr,
-                            cp, mk, r.c + slot * R * H, r.h + slot * R * H, R, H);
-        continue;
-      }
-      if (lstm_step_fwd_tc(cx, R, H, hp, WtS + D, D + H, nullptr, (save || has_x) ? g : nullptr, has_x, ptable,
-                           ptable ? r.gather + (int64_t)t * R : nullptr, cp, r.c + slot * R * H, r.h + slot * R * H, mk))
-        continue;
-      VD_REQUIRE(false, VD_E_STATE, "lstm_step_fwd_tc refused a shape the engine routed to it");
-    }
-    if (!save) {
-      const float* At = r.x ? r.x + (int64_t)t * R * D : A;
-      gemm_tn((int)R, G, D, At, lda, r.gather ? r.gather + (int64_t)t * R : nullptr, WtS, D + H, g, G, 0.f, nullptr, 0);
-    }
-    if (hp) gemm_tn((int)R, G, H, hp, H, nullptr, WtS + D, D + H, g, G, 1.f, nullptr, 0);
-    lstm_pointwise_fwd(cx, g, bias, cp, r.mask ? r.mask + (int64_t)t * R : nullptr, r.c + slot * R * H,
-                       r.h + slot * R * H, R, H);
-  }
 }
 
-void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last, float* dx_out,
-                           float* dh0_out, float* dc0_out) {
+void Engine::lstm_forward_step(LstmRun& r, int t) {
+  const int H = r.H, D = r.D, G = 4 * r.H;
+  const int64_t R = r.R;
+  const bool save = r.saved;
+  const float* WtS = Wtp(r.wseg);
+  const float* bias = Wp(r.wseg + 1);
+  const float* A = r.x ? r.x : Wp(0);
+  const int64_t lda = r.x ? D : cfg.E;
+  const float* xbias = r.tc ? bias : nullptr;
+  const int64_t slot = save ? t : (t & 1), pslot = save ? t - 1 : ((t - 1) & 1);
+  float* g = save ? r.gates + (int64_t)t * R * G : r.gates;
+  const float* hp = t > 0 ? r.h + pslot * R * H : r.h0;
+  const float* cp = t > 0 ? r.c + pslot * R * H : r.c0;
+  const bool per_step_x = !r.ptable && (!save || (r.tc && r.step_xproj));
+  LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * (H + ((r.ptable || per_step_x) ? D : 0)), 4.0 * R * (G + 4.0 * H));
+  if (r.tc) {
+    const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
+    int has_x = 0;
+    if (!r.ptable) {
+      if (per_step_x) gemm_tn((int)R, G, D, r.x + (int64_t)t * R * D, lda, nullptr, WtS, D + H, g, G, 0.f, xbias, 0);
+      has_x = 1;
+    }
+    const int32_t* tok = r.ptable ? r.gather + (int64_t)t * R : nullptr;
+    if (!hp) {          // t = 0 without h0: no recurrent term, a plain streaming kernel (x-projection already has the bias)
+      lstm_first_step_fwd(cx, (save || has_x) ? g : nullptr, r.ptable, tok, nullptr, cp, mk, r.c + slot * R * H,
+                          r.h + slot * R * H, R, H);
+      return;
+    }
+    bool ok = lstm_step_fwd_tc(cx, R, H, hp, WtS + D, D + H, nullptr, (save || has_x) ? g : nullptr, has_x, r.ptable, tok, cp,
+                               r.c + slot * R * H, r.h + slot * R * H, mk);
+    VD_REQUIRE(ok, VD_E_STATE, "lstm_step_fwd_tc refused a shape the engine routed to it");
+    return;
+  }
+  if (!save) {
+    const float* At = r.x ? r.x + (int64_t)t * R * D : A;
+    gemm_tn((int)R, G, D, At, lda, r.gather ? r.gather + (int64_t)t * R : nullptr, WtS, D + H, g, G, 0.f, nullptr, 0);
+  }
+  if (hp) gemm_tn((int)R, G, H, hp, H, nullptr, WtS + D, D + H, g, G, 1.f, nullptr, 0);
+  lstm_pointwise_fwd(cx, g, bias, cp, r.mask ? r.mask + (int64_t)t * R : nullptr, r.c + slot * R * H, r.h + slot * R * H, R, H);
+}
+
+void Engine::lstm_forward(LstmRun& r, bool save) {
+  lstm_forward_begin(r, save);
+  for (int t = 0; t < r.T; ++t) lstm_forward_step(r, t);
+}
+
+cudaEvent_t Engine::pool_event(size_t i) {
+  while (ev_pool.size() <= i) {
+    cudaEvent_t e;
+    VD_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_pool.push_back(e);
+  }
+  return ev_pool[i];
+}
+
+// Wavefront over two stacked layers: layer-2 step t only needs layer-1 step t, so the two recurrences run one step
+// apart on two streams instead of back to back (the per-step kernels of these 320-row LSTMs are latency-bound).
+void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb) {
+  const bool pipelined = math_mode == VD_MATH_TF32 && l2.H % 64 == 0 && sb != nullptr && sb != sa;
+  cx.stream = sa;
+  if (!pipelined) {
+    lstm_forward(l1, true);
+    l2.x = l1.h;
+    lstm_forward(l2, true);
+    return;
+  }
+  lstm_forward_begin(l1, true);
+  l2.x = l1.h;
+  l2.step_xproj = true;
+  cudaEvent_t e0 = pool_event(0);
+  VD_CUDA_CHECK(cudaEventRecord(e0, sa));
+  VD_CUDA_CHECK(cudaStreamWaitEvent(sb, e0, 0));
+  cx.stream = sb;
+  lstm_forward_begin(l2, true);
+  for (int t = 0; t < l1.T; ++t) {
+    cx.stream = sa;
+    lstm_forward_step(l1, t);
+    cudaEvent_t e = pool_event(1 + t);
+    VD_CUDA_CHECK(cudaEventRecord(e, sa));
+    VD_CUDA_CHECK(cudaStreamWaitEvent(sb, e, 0));
+    cx.stream = sb;
+    lstm_forward_step(l2, t);
+  }
+  VD_CUDA_CHECK(cudaEventRecord(e0, sb));
+  VD_CUDA_CHECK(cudaStreamWaitEvent(sa, e0, 0));
+  cx.stream = sa;
+}
+
+void Engine::lstm_backward_begin(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last) {
   VD_REQUIRE(r.saved, VD_E_STATE, "lstm_backward needs a forward run in training mode");
+  const int H = r.H, G = 4 * r.H;
+  const int64_t R = r.R, TR = (int64_t)r.T * R;
+  r.da = arena.get<float>(TR * G);
+  r.dc_carry = arena.get<float>(R * H);
+  r.dh_rec = arena.get<float>(R * H);
+  r.bw_dh_all = dh_all; r.bw_dh_last = dh_last; r.bw_dc_last = dc_last;
+  r.bw_tc = math_mode == VD_MATH_TF32 && H % 128 == 0;
+  if (r.bw_tc && dc_last)
+    VD_CUDA_CHECK(cudaMemcpyAsync(r.dc_carry, dc_last, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
+  else
+    VD_CUDA_CHECK(cudaMemsetAsync(r.dc_carry, 0, (size_t)R * H * sizeof(float), cx.stream));
+}
+
+void Engine::lstm_backward_step(LstmRun& r, int t) {
+  const int H = r.H, D = r.D, G = 4 * r.H;
+  const int64_t R = r.R;
+  const float* Ws = Wp(r.wseg);            // (D+H, 4H)
+  const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
+  const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
+  float* da_t = r.da + (int64_t)t * R * G;
+  const bool last = t == r.T - 1;
+  const float* ext = r.bw_dh_all ? r.bw_dh_all + (int64_t)t * R * H : nullptr;
+  LaunchCtx::Scope sc(&cx, "lstm_step_bwd", last ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
+  if (r.bw_tc) {
+    // one fused kernel per step: dh_rec = da_{t+1} Wh on tcgen05, backward pointwise in the epilogue
+    if (last) {         // no recurrent gradient yet: pointwise only (dh_last rides in the recurrent slot)
+      lstm_pointwise_bwd(cx, r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, r.bw_dh_last, ext, nullptr, r.dc_carry, mk,
+                         da_t, R, H);
+      return;
+    }
+    bool ok = lstm_step_bwd_tc(cx, R, H, r.da + (int64_t)(t + 1) * R * G, Ws + (int64_t)D * G, r.gates + (int64_t)t * R * G, cp,
+                               r.c + (int64_t)t * R * H, ext, r.dc_carry, mk, da_t);
+    VD_REQUIRE(ok, VD_E_STATE, "lstm_step_bwd_tc refused a shape the engine routed to it");
+    return;
+  }
+  const float* rec = last ? r.bw_dh_last : r.dh_rec;
+  lstm_pointwise_bwd(cx, r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, rec, ext, last ? r.bw_dc_last : nullptr,
+                     r.dc_carry, mk, da_t, R, H);
+  if (t > 0) gemm_tn((int)R, H, G, da_t, G, nullptr, Ws + (int64_t)D * G, G, r.dh_rec, H, 0.f, nullptr, 0);
+}
+
+void Engine::lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float* dc0_out) {
   const int H = r.H, D = r.D, G = 4 * r.H;
   const int64_t R = r.R, TR = (int64_t)r.T * R;
-  const float* Ws = Wp(r.wseg);            // (D+H, 4H)
-  float* da = arena.get<float>(TR * G);
-  float* dc_carry = arena.get<float>(R * H);
-  float* dh_rec = arena.get<float>(R * H);
-  VD_CUDA_CHECK(cudaMemsetAsync(dc_carry, 0, (size_t)R * H * sizeof(float), cx.stream));
-  const bool tc = math_mode == VD_MATH_TF32 && H % 128 == 0;
-  if (tc) {
-    // one fused kernel per step: dh_rec = da_{t+1} Wh on tcgen05, backward pointwise in the epilogue
-    if (dc_last) VD_CUDA_CHECK(cudaMemcpyAsync(dc_carry, dc_last, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
-    const float* ext_last = dh_all ? dh_all + (int64_t)(r.T - 1) * R * H : dh_last;
-    if (dh_all && dh_last) {
-      float* tmp = arena.get<float>(R * H);
-      add_out(cx, tmp, dh_all + (int64_t)(r.T - 1) * R * H, dh_last, R * H);
-      ext_last = tmp;
-    }
-    for (int t = r.T - 1; t >= 0; --t) {
-      const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
-      const float* ext = (t == r.T - 1) ? ext_last : (dh_all ? dh_all + (int64_t)t * R * H : nullptr);
-      LaunchCtx::Scope sc(&cx, "lstm_step_bwd", t == r.T - 1 ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
-      if (t == r.T - 1) {   // last step: no recurrent gradient yet, pointwise only
-        lstm_pointwise_bwd(cx, r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, nullptr, ext, nullptr, dc_carry,
-                           r.mask ? r.mask + (int64_t)t * R : nullptr, da + (int64_t)t * R * G, R, H);
-        continue;
-      }
-      bool ok = lstm_step_bwd_tc(cx, R, H, t == r.T - 1 ? nullptr : da + (int64_t)(t + 1) * R * G, Ws + (int64_t)D * G,
-                                 r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, ext, dc_carry,
-                                 r.mask ? r.mask + (int64_t)t * R : nullptr, da + (int64_t)t * R * G);
-      VD_REQUIRE(ok, VD_E_STATE, "lstm_step_bwd_tc refused a shape the engine routed to it");
-    }
-    if (dh0_out) gemm_tn((int)R, H, G, da, G, nullptr, Ws + (int64_t)D * G, G, dh0_out, H, 0.f, nullptr, 0);
-  }
-  for (int t = tc ? -1 : r.T - 1; t >= 0; --t) {
-    const float* cp = t > 0 ? r.c + (int64_t)(t - 1) * R * H : r.c0;
-    const float* rec = (t == r.T - 1) ? dh_last : dh_rec;
-    const float* ext = dh_all ? dh_all + (int64_t)t * R * H : nullptr;
-    float* da_t = da + (int64_t)t * R * G;
-    LaunchCtx::Scope sc(&cx, "lstm_step_bwd", 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
-    lstm_pointwise_bwd(cx, r.gates + (int64_t)t * R * G, cp, r.c + (int64_t)t * R * H, rec, ext,
-                       (t == r.T - 1) ? dc_last : nullptr, dc_carry, r.mask ? r.mask + (int64_t)t * R : nullptr, da_t, R, H);
-    float* dst = t > 0 ? dh_rec : dh0_out;
-    if (dst) gemm_tn((int)R, H, G, da_t, G, nullptr, Ws + (int64_t)D * G, G, dst, H, 0.f, nullptr, 0);
-  }
-  if (dc0_out) VD_CUDA_CHECK(cudaMemcpyAsync(dc0_out, dc_carry, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
+  const float* Ws = Wp(r.wseg);
+  float* da = r.da;
+  if (dh0_out) gemm_tn((int)R, H, G, da, G, nullptr, Ws + (int64_t)D * G, G, dh0_out, H, 0.f, nullptr, 0);
+  if (dc0_out) VD_CUDA_CHECK(cudaMemcpyAsync(dc0_out, r.dc_carry, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
   // accGradParameters
   float* dWs = dWp(r.wseg);
   const float* A = r.x ? r.x : Wp(0);
@@ -425,6 +487,53 @@ void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last
   gemm_atb(D, G, TR, A, lda, r.gather, da, G, dWs, G);
   colsum_add(cx, dWp(r.wseg + 1), da, TR, G, G);
   if (dx_out) gemm_tn((int)TR, D, G, da, G, nullptr, Ws, G, dx_out, D, 0.f, nullptr, 0);
+}
+
+void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last, float* dx_out,
+                           float* dh0_out, float* dc0_out) {
+  lstm_backward_begin(r, dh_all, dh_last, dc_last);
+  for (int t = r.T - 1; t >= 0; --t) lstm_backward_step(r, t);
+  lstm_backward_end(r, dx_out, dh0_out, dc0_out);
+}
+
+// BPTT wavefront of two stacked layers: layer-1 step t needs d(h1_t) = da2_t Wx2^T, produced per step on layer 2's
+// stream, so the two recurrences again run one step apart.
+void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2, const float* dc_last2, const float* dh_last1,
+                                const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb) {
+  const int H = l2.H, G = 4 * l2.H;
+  const int64_t R = l2.R;
+  float* dx2 = arena.get<float>((int64_t)l2.T * R * l2.D);      // = gradient wrt layer-1 outputs, all steps
+  const bool pipelined = math_mode == VD_MATH_TF32 && H % 128 == 0 && sb != nullptr && sb != sa;
+  cx.stream = sa;
+  if (!pipelined) {
+    lstm_backward(l2, nullptr, dh_last2, dc_last2, dx2, nullptr, nullptr);
+    lstm_backward(l1, dx2, dh_last1, dc_last1, dx1_out, nullptr, nullptr);
+    return;
+  }
+  const float* Wx2 = Wp(l2.wseg);            // rows 0..D2 of (D2+H, 4H): [N = D2, K = 4H]
+  cudaEvent_t e0 = pool_event(0);
+  VD_CUDA_CHECK(cudaEventRecord(e0, sa));
+  VD_CUDA_CHECK(cudaStreamWaitEvent(sb, e0, 0));
+  cx.stream = sb;
+  lstm_backward_begin(l2, nullptr, dh_last2, dc_last2);
+  cx.stream = sa;
+  lstm_backward_begin(l1, dx2, dh_last1, dc_last1);
+  for (int t = l2.T - 1; t >= 0; --t) {
+    cx.stream = sb;
+    lstm_backward_step(l2, t);
+    gemm_tn((int)R, l2.D, G, l2.da + (int64_t)t * R * G, G, nullptr, Wx2, G, dx2 + (int64_t)t * R * l2.D, l2.D, 0.f, nullptr, 0);
+    cudaEvent_t e = pool_event(1 + t);
+    VD_CUDA_CHECK(cudaEventRecord(e, sb));
+    VD_CUDA_CHECK(cudaStreamWaitEvent(sa, e, 0));
+    cx.stream = sa;
+    lstm_backward_step(l1, t);
+  }
+  cx.stream = sb;
+  lstm_backward_end(l2, nullptr, nullptr, nullptr);       // weight gradients of layer 2 (its dx was produced per step)
+  VD_CUDA_CHECK(cudaEventRecord(e0, sb));
+  cx.stream = sa;
+  lstm_backward_end(l1, dx1_out, nullptr, nullptr);
+  VD_CUDA_CHECK(cudaStreamWaitEvent(sa, e0, 0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -467,14 +576,10 @@ void Engine::encoder_forward(const vd_batch* b) {
     hist2 = make_run(db.Th, N, H, H, seg("hist.lstm2.weight"), nullptr, nullptr, ids_h);
   }
   // The 2nd layer consumes every step of the 1st, so encoder LSTMs always keep all steps (T*N*H is small).
-  auto run_two = [&](LstmRun& l1, LstmRun& l2) {
-    lstm_forward(l1, true);
-    l2.x = l1.h;
-    lstm_forward(l2, true);
-  };
+  auto run_two = [&](LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb) { lstm_pair_forward(l1, l2, sa, sb); };
   // The history and question LSTM chains are independent until the fusion/attention stage: the history chain runs
   // on the side stream (its tiny per-step kernels are latency-bound; overlapping the two chains hides half of it).
-  if (cfg.useHist) { fork_side(); run_two(hist1, hist2); back_to_main(); }
+  if (cfg.useHist) { fork_side(); run_two(hist1, hist2, side_stream, side2_stream); back_to_main(); }
   // question branch
   xq = arena.get<float>(N * db.Tq * E);
   embed_rows(cx, xq, Wp(0), ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
@@ -492,7 +597,7 @@ void Engine::encoder_forward(const vd_batch* b) {
     ques1 = make_run(db.Tq, N, E, H, seg("ques.lstm1.weight"), xq, nullptr, ids_q);
   }
   ques2 = make_run(db.Tq, N, H, H, seg("ques.lstm2.weight"), nullptr, nullptr, ids_q);
-  run_two(ques1, ques2);
+  run_two(ques1, ques2, main_stream, main2_stream);
   join_side();
   const float* q3 = ques2.h_last();
   const float* h3 = cfg.useHist ? hist2.h_last() : nullptr;
@@ -662,19 +767,15 @@ void Engine::encoder_backward(const float* dEnc) {
   const bool embdrop = cfg.enc == ENC_MN_ATT;
   if (cfg.useHist) {
     fork_side();
-    float* dx2 = arena.get<float>(N * db.Th * H);
-    lstm_backward(hist2, nullptr, dh3, nullptr, dx2, nullptr, nullptr);
     float* dx1 = arena.get<float>(N * db.Th * E);
-    lstm_backward(hist1, dx2, nullptr, nullptr, dx1, nullptr, nullptr);
+    lstm_pair_backward(hist1, hist2, dh3, nullptr, nullptr, nullptr, dx1, side_stream, side2_stream);
     embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
     back_to_main();
   }
   {
-    float* dx2 = arena.get<float>(N * db.Tq * H);
-    lstm_backward(ques2, nullptr, dq3, conn_dc_l2, dx2, nullptr, nullptr);
     int D1 = ques1.D;
     float* dx1 = arena.get<float>(N * db.Tq * D1);
-    lstm_backward(ques1, dx2, conn_dh_l1, conn_dc_l1, dx1, nullptr, nullptr);
+    lstm_pair_backward(ques1, ques2, dq3, conn_dc_l2, conn_dh_l1, conn_dc_l1, dx1, main_stream, main2_stream);
     embed_scatter_add(cx, dWp(0), dx1, D1, ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
     if (cfg.enc == ENC_HREA) {
       float* die = arena.get<float>(N * cfg.IE);

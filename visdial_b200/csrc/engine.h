@@ -55,6 +55,14 @@ struct LstmRun {
   const float* h0 = nullptr; const float* c0 = nullptr;
   float* h = nullptr; float* c = nullptr; float* gates = nullptr;
   bool saved = false;
+  // forward run state (lstm_forward_begin / _step)
+  bool tc = false;                   // fused tcgen05 step kernels
+  bool step_xproj = false;           // dense input projected per step (layer-2 of a pipelined pair) instead of batched
+  const float* ptable = nullptr;     // (V+1, 4H) projection table for embedding-gathered inputs
+  // backward run state (lstm_backward_begin / _step / _end)
+  float* da = nullptr; float* dc_carry = nullptr; float* dh_rec = nullptr;
+  const float* bw_dh_all = nullptr; const float* bw_dh_last = nullptr; const float* bw_dc_last = nullptr;
+  bool bw_tc = false;
   const float* h_last() const { return h + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
   const float* c_last() const { return c + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
 };
@@ -145,6 +153,18 @@ struct Engine {
   void refresh_shadows();
   void stage_batch(const vd_batch* b);
   void lstm_forward(LstmRun& r, bool save);
+  void lstm_forward_begin(LstmRun& r, bool save);
+  void lstm_forward_step(LstmRun& r, int t);
+  void lstm_backward_begin(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last);
+  void lstm_backward_step(LstmRun& r, int t);
+  void lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float* dc0_out);
+  // two stacked SeqLSTMs as a wavefront: layer 2 step t runs (on its own stream) as soon as layer 1 step t is done
+  void lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb);
+  void lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2, const float* dc_last2, const float* dh_last1,
+                          const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb);
+  cudaStream_t main2_stream = nullptr, side2_stream = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t pool_event(size_t i);
   void lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last, float* dx_out,
                      float* dh0_out, float* dc0_out);
 

@@ -903,7 +903,8 @@ bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t
   if (M < 32 || N < 32 || K < 64) return false;
   if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
   const int tiles = cdiv(M, BM) * cdiv(N, ATB_BN);
-  int64_t splits = std::max<int64_t>(1, std::min<int64_t>((2LL * cx.sm_count + tiles - 1) / tiles, K / (ATB_KB * 4)));
+  // whole waves: the largest split count with tiles * splits <= 2 * #SM (one CTA per SM at this smem footprint)
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>((2LL * cx.sm_count) / tiles, K / (ATB_KB * 4)));
   int64_t kps = ((K + splits - 1) / splits + ATB_KB - 1) / ATB_KB * ATB_KB;
   splits = (K + kps - 1) / kps;
   AtbParams p = {M, N, K, kps, C, ldc};
