@@ -255,7 +255,7 @@ def run_ours(args, rank, local, world):
     ms_dev, wall_dev, launches = timed(dev_loader, args.steps, not args.ncu_range)
     if args.ncu_range:
         eng.profiler_range(False)
-    stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS + ("gemm", "gemm_wgrad", "allreduce")}
+    stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS + ("lstm_step_small", "lstm_step_bwd_small", "gemm", "gemm_wgrad", "embed_grad_segsum", "allreduce")}
     ms_e2e, wall_e2e, _ = timed(host_loader, args.steps, False)
     if rank == 0:
         sampler.mark_end()
@@ -275,7 +275,7 @@ def run_ours(args, rank, local, world):
     fl = sum(stats[k]["flops"] for k in LSTM_STEP_KEYS)
     t_ms = sum(stats[k]["ms"] for k in LSTM_STEP_KEYS)
     achieved = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "lstm_step (recurrent gate GEMM + pointwise, fwd and bwd)",
+    roofline = {"bound": "tensor", "kernel": "k_tc_gemm<256,LSTM_FWD|LSTM_BWD,2>: option-LSTM step (recurrent gate GEMM on tcgen05 + SeqLSTM pointwise epilogue), 19 fwd + 19 bwd launches per training step",
                 "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 operands)" % peaks["src"],
                 "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / max(ms_dev, 1e-9),

@@ -331,7 +331,9 @@ void Engine::lstm_forward_step(LstmRun& r, int t) {
   const float* hp = t > 0 ? r.h + pslot * R * H : r.h0;
   const float* cp = t > 0 ? r.c + pslot * R * H : r.c0;
   const bool per_step_x = !r.ptable && (!save || (r.tc && r.step_xproj));
-  LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * (H + ((r.ptable || per_step_x) ? D : 0)), 4.0 * R * (G + 4.0 * H));
+  // the big (option-LSTM) launches run alone on the GPU: they are the roofline kernel class; the 320-row encoder
+  // steps overlap on 4 streams and are accounted separately
+  LaunchCtx::Scope sc(&cx, R >= 4096 ? "lstm_step" : "lstm_step_small", 2.0 * R * G * (H + ((r.ptable || per_step_x) ? D : 0)), 4.0 * R * (G + 4.0 * H));
   if (r.tc) {
     const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
     int has_x = 0;
@@ -429,7 +431,7 @@ void Engine::lstm_backward_step(LstmRun& r, int t) {
   float* da_t = r.da + (int64_t)t * R * G;
   const bool last = t == r.T - 1;
   const float* ext = r.bw_dh_all ? r.bw_dh_all + (int64_t)t * R * H : nullptr;
-  LaunchCtx::Scope sc(&cx, "lstm_step_bwd", last ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
+  LaunchCtx::Scope sc(&cx, R >= 4096 ? "lstm_step_bwd" : "lstm_step_bwd_small", last ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
   if (r.bw_tc) {
     // one fused kernel per step: dh_rec = da_{t+1} Wh on tcgen05, backward pointwise in the epilogue
     if (last) {         // no recurrent gradient yet: pointwise only (dh_last rides in the recurrent slot)
