@@ -230,7 +230,7 @@ int vd_timer_stop(vd_engine* h, float* ms) {
     VD_CUDA_CHECK(cudaEventElapsedTime(ms, e->t0, e->t1));
   })
 }
-int vd_profile_enable(vd_engine* h, int32_t on) { VD_TRY({ ENG(h)->cx.profiling = on != 0; }) }
+int vd_profile_enable(vd_engine* h, int32_t on) { VD_TRY({ ENG(h)->cx.profiling = on; }) }
 int vd_profile_reset(vd_engine* h) {
   VD_TRY({ Engine* e = ENG(h); e->cx.collect(); e->cx.stats.clear(); e->cx.launches = 0; })
 }

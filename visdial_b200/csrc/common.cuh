@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <stdexcept>
 #include <vector>
@@ -97,7 +98,7 @@ struct KStat {
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
-  bool profiling = false;
+  int profiling = 0;          // 0 off, 1 every class, 2 only the roofline class (big lstm_step / lstm_step_bwd launches)
   int sm_count = 148;
   std::map<std::string, KStat> stats;
   std::vector<cudaEvent_t> free_events;
@@ -111,6 +112,7 @@ struct LaunchCtx {
     LaunchCtx* cx; KStat* st; cudaEvent_t a = nullptr, b = nullptr;
     Scope(LaunchCtx* c, const char* name, double flops, double bytes) : cx(c), st(nullptr) {
       if (!cx->profiling) return;
+      if (cx->profiling == 2 && strcmp(name, "lstm_step") != 0 && strcmp(name, "lstm_step_bwd") != 0) return;
       st = &cx->stats[name];
       st->launches++; st->flops += flops; st->bytes += bytes;
       a = cx->get_event(); b = cx->get_event();
