@@ -139,6 +139,13 @@ def max_over_ranks(x, world):
     return vdist.max_over_ranks(x)
 
 
+def cpu_threads(args):
+    """Threads for the CPU arm.  The reference structure is a chain of small per-timestep addmm / pointwise ops
+    (N = 10 rows per dialog): measured on the 128-vCPU GPU host it is FASTEST with 8 threads (2.8 s/step at B=1;
+    32 threads: 4.1 s; 128 threads: minutes, oversubscribed), so 8 is what "all the threads it can use" means."""
+    return max(1, min(args.cpu_threads, os.cpu_count() or 1))
+
+
 def cpu_oracle_step_time(B, steps, warmup, structure, threads):
     """Seconds per training step of the oracle on B dialogs (forward, backward, clamp+adam)."""
     import torch
@@ -170,7 +177,7 @@ def run_reference(args, rank, world):
     addmm, 100 sequential option-LSTM passes, materialised repeatTensor), all host threads, bounded sample."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads(args)
     B = args.ref_batch
     sec, p = cpu_oracle_step_time(B, args.steps, min(args.warmup, 1), "reference", threads)
     val = B * 10 / sec
@@ -308,7 +315,7 @@ def run_ours(args, rank, local, world):
             "kernel_ms": breakdown,
             "wall_ms_per_step": wall_dev / args.steps}
     if world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads(args)
         sec, _ = cpu_oracle_step_time(args.cpu_batch, 1, 1, "reference", threads)
         line["cpu_baseline"] = {"value": args.cpu_batch * 10 / sec, "unit": "QA-rounds/s", "cores": threads, "kind": "port",
                                 "sample": "%d dialogs (%d QA rounds), 1 warm-up + 1 timed step of the oracle in reference "
@@ -326,6 +333,7 @@ def main():
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--ref-batch", type=int, default=1)
+    ap.add_argument("--cpu-threads", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ncu-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop")
     args = ap.parse_args()
