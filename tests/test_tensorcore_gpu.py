@@ -211,3 +211,29 @@ def test_tf32_cta_pair_kernels_match_oracle():
         s = seg_slices(p)[name]
         assert _rel(g[s], ref["grads"][name].numpy()) < 2e-2, name
     eng.close()
+
+
+@pytest.mark.parametrize("enc,dec,B", [("hrea-ques-im-hist", "gen", 2), ("lf-ques-im-hist", "disc", 2), ("lf-ques", "gen", 4)])
+def test_tf32_other_configs_at_reference_layer_sizes(enc, dec, B):
+    """BASELINE configs 1-3 at the reference's real layer sizes (E=300, H=512, fc7 4096, V=10000 / 1000)."""
+    p = full_params(enc, dec, vocabSize=1000 if enc == "lf-ques" else 10000)
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, B, seed=5, max_hist_concat=80)
+    eng = Engine(p)
+    eng.set_math_mode(VD_MATH_TF32)
+    eng.set_parameters(flat)
+    eng.set_training(1)
+    eng.set_dropout_seed(11, 3)
+    eng.zero_grad()
+    loss = eng.forward_backward(Batch(nb))
+    g = eng.get_gradients()
+    psite = {O.SITE_FUSION: p["dropout"]}
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3, psite), structure="batched"), p,
+                             torch_params(p, flat), torch_batch(nb))
+    assert abs(loss - ref["loss"]) < 5e-3 * max(1.0, abs(ref["loss"])), (loss, ref["loss"])
+    for name, s in seg_slices(p).items():
+        r = ref["grads"][name].numpy().ravel()
+        if np.abs(r).max() < 1e-6:
+            continue
+        assert _rel(g[s], r) < 3e-2, name
+    eng.close()
