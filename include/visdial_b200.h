@@ -178,6 +178,65 @@ int vd_profiler_range(vd_engine* e, int32_t start);
 /* flush L2 by writing a scratch buffer larger than L2 (bench hygiene) */
 int vd_flush_l2(vd_engine* e);
 
+/* ---- dataloader: HBM-resident corpus and on-device batch assembly --------------------------------
+ * Replaces dataloader:initialize's tensor preparation and the per-batch indexing
+ * (dataloader.lua:143-321 prepareDataset / processAnswers / processHistory / processOptions,
+ * utils.lua:6-45 rightAlign, dataloader.lua:324-478 getTrainBatch / getTestBatch / getIndexData /
+ * getIndexOption).  The raw arrays are the datasets of visdial_data.h5 for ONE split exactly as
+ * data/prepro.py:105-183 writes them (the HDF5 read itself stays with the host language); they are
+ * uploaded once, prepared on the device, and every later batch is gathered + trimmed on the device:
+ * per batch only the dialog indices cross PCIe.  All ids int32, 1-based with 0 = pad. */
+typedef struct vd_corpus vd_corpus;
+
+typedef struct vd_corpus_desc {
+  int32_t numThreads;           /* dialogs in the split: ques:size(1)                      (dataloader.lua:94-105) */
+  int32_t numRounds;            /* ques:size(2) = maxQuesCount                             (:122)  */
+  int32_t maxQuesLen;           /* ques:size(3)                                            (:124)  */
+  int32_t maxAnsLen;            /* ans:size(3) = opt_list:size(2)                          (:126)  */
+  int32_t maxCapLen;            /* cap:size(2); must be >= maxQuesLen + maxAnsLen when useHistory (:236) */
+  int32_t numOptions;           /* opt:size(3)                                             (:112)  */
+  int32_t numOptList;           /* opt_list:size(1)                                                */
+  int32_t numImages;            /* images:size(1)                                                  */
+  int32_t useHistory;           /* opt.useHistory / concatHistory / useIm                  (:139-141) */
+  int32_t concatHistory;
+  int32_t useIm;
+  int32_t maxHistoryLen;        /* opt.maxHistoryLen (60) — overwritten by min(R*(Lq+La),300) when concatHistory (:142,:217) */
+  int32_t imgNorm;              /* 1: L2-normalise over dim 2 at load                      (:64-68) */
+  int32_t imgAtt;               /* 1: images are (N,C,S,S) and are stored (N,S,S,C)        (:70-72) */
+  int32_t imgChannels;          /* C (pool5 512) or F (fc7 4096)                                   */
+  int32_t imgSpatial;           /* S (14); ignored unless imgAtt                                   */
+  int32_t startToken, endToken; /* word2ind['<START>'], word2ind['<END>']                  (:17-22) */
+  const int32_t* ques;          /* (n,R,Lq) left-aligned  'ques_<split>'                           */
+  const int32_t* ques_len;      /* (n,R)                  'ques_length_<split>'                    */
+  const int32_t* ans;           /* (n,R,La)               'ans_<split>'                            */
+  const int32_t* ans_len;       /* (n,R)                  'ans_length_<split>'                     */
+  const int32_t* cap;           /* (n,Lc)                 'cap_<split>'        (NULL unless useHistory) */
+  const int32_t* cap_len;       /* (n)                    'cap_length_<split>'                     */
+  const int32_t* opt;           /* (n,R,K) 1-based rows of opt_list  'opt_<split>'                 */
+  const int32_t* opt_list;      /* (m,La)                 'opt_list_<split>'                       */
+  const int32_t* opt_len;       /* (m)                    'opt_length_<split>'                     */
+  const int32_t* ans_index;     /* (n,R) 1-based gt option 'ans_index_<split>' (NULL for test)     */
+  const int32_t* img_pos;       /* (n) 0-based row of images as stored ('img_pos_<split>'; the +1 of :76-77 is Lua indexing) */
+  const int32_t* num_rounds;    /* (n)                    'num_rounds_<split>' (may be NULL)       */
+  const float* images;          /* (N,F) or (N,C,S,S) fp32 'images_<split>' of the image h5 (NULL unless useIm) */
+} vd_corpus_desc;
+
+/* dataloader:initialize tensors -> HBM + dataloader:prepareDataset on the device.  Host pointers. */
+int vd_corpus_create(vd_engine* e, const vd_corpus_desc* d, vd_corpus** out);
+int vd_corpus_destroy(vd_corpus* c);
+/* Assemble the batch of dialogs `inds` (HOST array of n 0-based dialog indices = Lua's inds - 1) on the engine's stream.
+ *   decoder_gen = 0: getIndexData + getIndexOption('disc')  -> ques_fwd, hist, img_feat, answer_in/out, answer_ind, options
+ *   decoder_gen = 1: getIndexData only (getTrainBatch, gen)  -> ... without options
+ *   decoder_gen = 2: getIndexData + getIndexOption('gen')   -> ... plus option_in / option_out (getTestBatch, gen)
+ * `out` receives DEVICE pointers (on_device = 1) into corpus-owned buffers that stay valid until the second-next
+ * vd_corpus_get_batch on this corpus (two buffer sets, alternating). */
+int vd_corpus_get_batch(vd_corpus* c, const int64_t* inds, int32_t n, int32_t decoder_gen, vd_batch* out);
+/* Read one PREPARED tensor back to the host (parity tests): name in {"ques_fwd","hist","hist_len","ans_in","ans_out",
+ * "opt_in","opt_out","img_fv"}; *elems receives the element count (call with host_dst = NULL to size). */
+int vd_corpus_read(vd_corpus* c, const char* name, void* host_dst, int64_t* elems);
+/* bytes the last vd_corpus_get_batch read + wrote in HBM (algorithmic) and the number of kernels it launched */
+int vd_corpus_batch_bytes(vd_corpus* c, int64_t* bytes, int32_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,163 @@
+"""Device-resident corpus + on-device batch assembly (visdial_b200/csrc/corpus.cu through the C ABI) against
+oracle/dataloader_oracle.py — bit-exact for every integer tensor, 1e-6 relative for the normalised image features.
+Reference: /root/reference/dataloader.lua:143-478, utils.lua:6-45."""
+import numpy as np
+import pytest
+
+from oracle import dataloader_oracle as D
+from helpers import small_params
+from visdial_b200._lib import VdError
+from visdial_b200.dataloader import Dataloader
+from visdial_b200.engine import Batch, Engine
+from visdial_b200.model import Model
+from visdial_b200.synthetic import make_corpus
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [("lf-ques", "gen"), ("lf-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "disc"),
+           ("lf-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "gen")]
+
+
+def _opt(params, img_norm):
+    enc = params["encoder"]
+    return dict(params, useHistory="hist" in enc, concatHistory="lf" in enc, useIm="im" in enc,
+                maxHistoryLen=60, imgNorm=int(img_norm))
+
+
+def _setup(enc, dec, n=40, m=300, img_norm=True, seed=11, **kw):
+    params = small_params(enc, dec)
+    concat = "lf" in enc and "hist" in enc
+    raw = make_corpus(params, n, m, seed=seed, ques_len_cap=14 if concat else None, ans_len_cap=13 if concat else None, **kw)
+    opt = _opt(params, img_norm)
+    V = params["vocabSize"]
+    orc = D.DataloaderOracle(raw, use_history=opt["useHistory"], concat_history=opt["concatHistory"], use_im=opt["useIm"],
+                             start=V - 1, end=V, img_norm=img_norm, att="att" in enc)
+    eng = Engine(params)
+    dl = Dataloader(eng, seed=5).initialize(opt, ["train", "val"], {"train": raw, "val": raw})
+    return params, raw, orc, eng, dl
+
+
+def _same_batch(dev, ref, keys_float=("img_feat",)):
+    got = dev.numpy()
+    want_keys = {k for k in ref if k != "num_rounds"}
+    assert set(got) == want_keys, (sorted(got), sorted(want_keys))
+    for k in want_keys:
+        if k in keys_float:
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-6, atol=1e-7, err_msg=k)
+        else:
+            assert got[k].shape == ref[k].shape, (k, got[k].shape, ref[k].shape)
+            assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("enc,dec", CONFIGS)
+def test_prepared_tensors_match_oracle(enc, dec):
+    params, raw, orc, eng, dl = _setup(enc, dec)
+    c = dl.corpus["train"]
+    n, R = raw["ques"].shape[:2]
+    assert np.array_equal(c.read("ques_fwd").reshape(orc.ques_fwd.shape), orc.ques_fwd)
+    assert np.array_equal(c.read("ans_in").reshape(orc.ans_in.shape), orc.ans_in)
+    assert np.array_equal(c.read("ans_out").reshape(orc.ans_out.shape), orc.ans_out)
+    assert np.array_equal(c.read("opt_in").reshape(orc.opt_in.shape), orc.opt_in)
+    assert np.array_equal(c.read("opt_out").reshape(orc.opt_out.shape), orc.opt_out)
+    if "hist" in enc:
+        assert np.array_equal(c.read("hist_len").reshape(n, R), orc.hist_len)
+        assert np.array_equal(c.read("hist").reshape(orc.hist.shape), orc.hist)
+        assert dl.maxHistoryLen == orc.maxHistoryLen
+    if "im" in enc:
+        np.testing.assert_allclose(c.read("img_fv").reshape(orc.img_fv.shape), orc.img_fv, rtol=1e-6, atol=1e-7)
+    dl.close(); eng.close()
+
+
+@pytest.mark.parametrize("enc,dec", CONFIGS)
+def test_batches_match_oracle(enc, dec):
+    params, raw, orc, eng, dl = _setup(enc, dec)
+    n = raw["ques"].shape[0]
+    rng = np.random.default_rng(0)
+    cases = [np.arange(0, 8), np.array([6, 6, 7, 39, 6]), rng.integers(0, n, size=32), np.array([9])]
+    for inds in cases:
+        for mode, kw in ((0 if dec == "disc" else 1, dict(test_batch=False)), (0 if dec == "disc" else 2, dict(test_batch=True))):
+            dev = dl.corpus["train"].get_batch(inds, mode)
+            _same_batch(dev, orc.get_batch(inds, dec, **kw))
+            assert dev.num_answer_tokens == int((orc.get_batch(inds, dec, **kw)["answer_out"] > 0).sum())
+    # getTestBatch walks the split in order and the last batch is ragged (dataloader.lua:347-357)
+    p = dict(params, batchSize=16)
+    start, seen = 0, 0
+    while start < n:
+        dev, nxt = dl.getTestBatch(start, p, "val")
+        ref = orc.get_batch(np.arange(start, nxt), dec, test_batch=True)
+        _same_batch(dev, ref)
+        assert np.array_equal(dev["num_rounds"], ref["num_rounds"])
+        seen += dev.c.B; start = nxt
+    assert seen == n
+    by, launches = dl.corpus["val"].batch_bytes()
+    assert launches == (2 if "im" in enc else 1) and by > 0
+    dl.close(); eng.close()
+
+
+def test_unnormalised_fc7_and_shared_images():
+    # imgNorm = 0 and several dialogs pointing at the same image row (img_pos is an arbitrary map, dataloader.lua:395-397)
+    params, raw, orc, eng, dl = _setup("lf-ques-im-hist", "disc", img_norm=False, num_images=7)
+    inds = np.arange(0, 20)
+    _same_batch(dl.corpus["train"].get_batch(inds, 0), orc.get_batch(inds, "disc", test_batch=False), keys_float=())
+    dl.close(); eng.close()
+
+
+def test_two_batches_stay_valid():
+    # the corpus alternates two output sets: batch k is still intact after batch k+1 has been assembled
+    params, raw, orc, eng, dl = _setup("mn-att-ques-im-hist", "disc")
+    a = dl.corpus["train"].get_batch(np.arange(0, 8), 0)
+    b = dl.corpus["train"].get_batch(np.arange(20, 30), 0)
+    _same_batch(a, orc.get_batch(np.arange(0, 8), "disc", test_batch=False))
+    _same_batch(b, orc.get_batch(np.arange(20, 30), "disc", test_batch=False))
+    dl.close(); eng.close()
+
+
+def test_errors_are_reported_not_swallowed():
+    params = small_params("lf-ques-im-hist", "disc")
+    raw = make_corpus(params, 16, 50, seed=2)              # full-length rounds: concat history exceeds 300 tokens
+    eng = Engine(params)
+    with pytest.raises(VdError):                           # dataloader.lua:246-253 would raise an index error
+        Dataloader(eng).initialize(_opt(params, True), ["train"], {"train": raw})
+    raw = make_corpus(params, 16, 50, seed=2, ques_len_cap=14, ans_len_cap=13)
+    bad = dict(raw); bad["opt"] = raw["opt"].copy(); bad["opt"][3, 2, 1] = 51
+    with pytest.raises(VdError):
+        Dataloader(eng).initialize(_opt(params, True), ["train"], {"train": bad})
+    dl = Dataloader(eng).initialize(_opt(params, True), ["train"], {"train": raw})
+    with pytest.raises(VdError):
+        dl.corpus["train"].get_batch(np.array([16]), 0)
+    with pytest.raises(VdError):
+        dl.corpus["train"].get_batch(np.array([], dtype=np.int64), 0)
+    dl.close(); eng.close()
+
+
+@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen")])
+def test_training_from_device_batches_equals_host_batches(enc, dec):
+    """Model:trainIteration fed by the device dataloader == the same step fed by the oracle's host batch."""
+    params, raw, orc, eng, dl = _setup(enc, dec)
+    eng.close()
+    inds = np.array([0, 5, 9, 13, 21, 21, 30, 38])
+
+    class Fixed:
+        def __init__(self, fn): self.fn = fn
+        def getTrainBatch(self, p, B=None): return self.fn()
+
+    losses = []
+    for source in ("device", "host"):
+        model = Model(dict(params, batchSize=len(inds)), seed=7)
+        model.engine.set_math_mode(1)
+        if source == "device":
+            d2 = Dataloader(model.engine).initialize(_opt(params, True), ["train"], {"train": raw})
+            feed = Fixed(lambda: d2.corpus["train"].get_batch(inds, 0 if dec == "disc" else 1))
+        else:
+            ref = orc.get_batch(inds, dec, test_batch=False)
+            feed = Fixed(lambda: Batch({k: v for k, v in ref.items()}))
+        losses.append([model.trainIteration(feed) for _ in range(3)])
+        w = model.engine.get_parameters()
+        losses[-1].append(w)
+        model.engine.close()
+    # the inputs differ only by the last-ulp of the normalised image features; Adam turns that into O(lr) noise on
+    # parameters whose gradient is ~0, so the parameters are compared in aggregate and the losses tightly
+    for a, b in zip(losses[0][:3], losses[1][:3]):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b))
+    d = np.abs(losses[0][3] - losses[1][3])
+    assert d.max() <= 7e-3 and (d > 1e-5).mean() < 1e-3

@@ -43,6 +43,16 @@ class vd_batch(C.Structure):
     ]
 
 
+class vd_corpus_desc(C.Structure):
+    _fields_ = ([(k, C.c_int32) for k in (
+        "numThreads", "numRounds", "maxQuesLen", "maxAnsLen", "maxCapLen", "numOptions", "numOptList", "numImages",
+        "useHistory", "concatHistory", "useIm", "maxHistoryLen", "imgNorm", "imgAtt", "imgChannels", "imgSpatial",
+        "startToken", "endToken")] +
+        [(k, C.c_void_p) for k in (
+            "ques", "ques_len", "ans", "ans_len", "cap", "cap_len", "opt", "opt_list", "opt_len", "ans_index",
+            "img_pos", "num_rounds", "images")])
+
+
 _P = C.POINTER
 _H = C.c_void_p  # vd_engine*
 
@@ -99,6 +109,11 @@ SIGNATURES = {
                     C.c_int64],
     "vd_profiler_range": [_H, C.c_int32],
     "vd_flush_l2": [_H],
+    "vd_corpus_create": [_H, _P(vd_corpus_desc), _P(C.c_void_p)],
+    "vd_corpus_destroy": [C.c_void_p],
+    "vd_corpus_get_batch": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(vd_batch)],
+    "vd_corpus_read": [C.c_void_p, C.c_char_p, C.c_void_p, _P(C.c_int64)],
+    "vd_corpus_batch_bytes": [C.c_void_p, _P(C.c_int64), _P(C.c_int32)],
 }
 
 _lib = None

@@ -8,6 +8,12 @@ namespace vd {
 void comm_unique_id(void* out);
 void comm_init(Engine* e, const void* idbytes, int rank, int world);
 void comm_destroy(Engine* e);
+struct Corpus;
+Corpus* corpus_create(Engine* eng, const vd_corpus_desc* d);
+void corpus_destroy(Corpus* c);
+void corpus_get_batch(Corpus* c, const int64_t* inds, int n, int decoder_gen, vd_batch* out);
+void corpus_read(Corpus* c, const char* name, void* host_dst, int64_t* elems);
+void corpus_batch_bytes(Corpus* c, int64_t* bytes, int32_t* launches);
 }  // namespace vd
 
 using vd::Engine;
@@ -284,6 +290,34 @@ int vd_flush_l2(vd_engine* h) {
     }
     vd::fill_l2_flush(e->cx, e->flush_buf, e->flush_n);
   })
+}
+
+// ---- dataloader: resident corpus (corpus.cu) ----
+struct vd_corpus { vd::Corpus* c; };
+#define CORP(h) ((h) ? (h)->c : (throw vd::CudaError(VD_E_BADARG, "corpus handle is null"), (vd::Corpus*)nullptr))
+
+int vd_corpus_create(vd_engine* h, const vd_corpus_desc* d, vd_corpus** out) {
+  VD_TRY({
+    NOTNULL(out);
+    Engine* e = ENG(h);
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    vd::Corpus* c = vd::corpus_create(e, d);
+    *out = new vd_corpus{c};
+  })
+}
+int vd_corpus_destroy(vd_corpus* h) {
+  VD_TRY({
+    if (h) { vd::corpus_destroy(h->c); delete h; }
+  })
+}
+int vd_corpus_get_batch(vd_corpus* h, const int64_t* inds, int32_t n, int32_t decoder_gen, vd_batch* out) {
+  VD_TRY({ vd::corpus_get_batch(CORP(h), inds, n, decoder_gen, out); })
+}
+int vd_corpus_read(vd_corpus* h, const char* name, void* host_dst, int64_t* elems) {
+  VD_TRY({ vd::corpus_read(CORP(h), name, host_dst, elems); })
+}
+int vd_corpus_batch_bytes(vd_corpus* h, int64_t* bytes, int32_t* launches) {
+  VD_TRY({ vd::corpus_batch_bytes(CORP(h), bytes, launches); })
 }
 
 }  // extern "C"

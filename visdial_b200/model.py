@@ -11,6 +11,19 @@ from .engine import Batch, DEFAULT_PARAMS, derive_flags
 from .modules import Criterion, Sequential
 
 
+def _as_batch(b):
+    """getTestBatch returns (batch, nextStartId) in the reference (dataloader.lua:375); accept either form."""
+    if isinstance(b, tuple):
+        b = b[0]
+    return b if isinstance(b, Batch) else Batch(b)
+
+
+def _num_tokens(batch) -> int:
+    """answerOut:gt(0):sum() (model.lua:78); device batches carry it from the host length table."""
+    n = getattr(batch, "num_answer_tokens", None)
+    return int(n) if n is not None else int((batch["answer_out"] > 0).sum())
+
+
 class Model:
     def __init__(self, params: dict, seed: int = 1234):                  # model.lua:11-62
         p = dict(DEFAULT_PARAMS)
@@ -48,7 +61,7 @@ class Model:
         self.engine.set_dropout_seed(self.params.get("seed", 1234), self.iteration)
         curLoss = self.forwardBackward(batch)                             # :74
         if self.params["decoder"] == "gen":                               # :76-85
-            numTokens = int((batch["answer_out"] > 0).sum())
+            numTokens = _num_tokens(batch)
             cur = curLoss / max(numTokens, 1)
         else:                                                             # :86-93
             cur = curLoss
@@ -97,10 +110,10 @@ class Model:
         curLoss, numTokens, n = 0.0, 0, 0
         numThreads = dataloader.numThreads[dtype]
         for startId in range(0, numThreads, self.params["batchSize"]):
-            batch = Batch(dataloader.getTestBatch(startId, self.params, dtype))
+            batch = _as_batch(dataloader.getTestBatch(startId, self.params, dtype))
             curLoss += self.forwardBackward(batch, True)
             if self.params["decoder"] == "gen":
-                numTokens += int((batch["answer_out"] > 0).sum())
+                numTokens += _num_tokens(batch)
             n += 1
         self.wrapper.training()
         return curLoss / max(numTokens, 1) if self.params["decoder"] == "gen" else curLoss / max(n, 1)
@@ -110,7 +123,7 @@ class Model:
         ranks = []
         numThreads = dataloader.numThreads[dtype]
         for startId in range(0, numThreads, self.params["batchSize"]):
-            batch = dataloader.getTestBatch(startId, self.params, dtype)
+            batch = _as_batch(dataloader.getTestBatch(startId, self.params, dtype))
             ranks.append(self.retrieveBatch(batch).reshape(-1, self.params["maxQuesCount"]))
         self.wrapper.training()
         return np.concatenate(ranks, 0)

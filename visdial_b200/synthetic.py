@@ -130,3 +130,62 @@ class SyntheticDataloader:
         B = int(params.get("batchSize", 40))
         return make_batch(params, B, seed=self.seed + 100003 + start_id,
                           gen_eval=params.get("decoder") == "gen")
+
+
+def make_corpus(params: dict, num_threads: int = 64, num_opt_list: int = 512, seed: int = 4321, max_ques_len: int = 20,
+                max_ans_len: int = 20, max_cap_len: int = 40, ques_len_cap: int = None, ans_len_cap: int = None,
+                edge_cases: bool = True, num_images: int = None) -> Dict[str, np.ndarray]:
+    """One split of visdial_data.h5 + data_img.h5 in the layout data/prepro.py:105-183 writes (dataset names without
+    the `_<split>` suffix): left-aligned zero-padded token matrices with separate length arrays, 1-based option rows
+    into `opt_list`, 1-based `ans_index`, 0-based `img_pos`.  `edge_cases` plants what the reference's loops treat
+    specially: an empty question / empty answer round in the middle of a dialog (utils.lua:20-22 `break`), an empty
+    caption, an empty option, and one dialog with every sequence at full length."""
+    rng = np.random.default_rng(seed)
+    V = int(params["vocabSize"])
+    R = int(params.get("maxQuesCount", 10))
+    K = int(params.get("numOptions", 100))
+    enc = params["encoder"]
+    n, m = int(num_threads), int(num_opt_list)
+    qcap = int(ques_len_cap or max_ques_len)
+    acap = int(ans_len_cap or max_ans_len)
+    tok = lambda shape: rng.integers(1, V - 1, size=shape, dtype=np.int32)
+    mask = lambda lens, width: (np.arange(width)[None, :] < np.asarray(lens).reshape(-1, 1)).astype(np.int32)
+
+    ques_len = rng.integers(1, qcap + 1, size=(n, R)).astype(np.int32)
+    ans_len = rng.integers(1, acap + 1, size=(n, R)).astype(np.int32)
+    cap_len = rng.integers(1, max_cap_len + 1, size=n).astype(np.int32)
+    opt_len = rng.integers(1, acap + 1, size=m).astype(np.int32)
+    if edge_cases and n >= 8:
+        ques_len[0, :], ans_len[0, :], cap_len[0] = qcap, acap, max_cap_len      # everything at full length
+        ques_len[1, 4] = 0                                                       # empty question mid-dialog
+        ans_len[2, 3] = 0                                                        # empty answer
+        ques_len[3, 2], ans_len[3, 2] = 0, 0                                     # empty Q and A -> empty history round
+        cap_len[4] = 0                                                           # empty caption
+        ques_len[5, R - 1], ans_len[5, R - 1] = 0, 0                             # v1.0-test style short dialog
+        opt_len[1] = 0                                                           # empty option
+    out = {
+        "ques": tok((n, R, max_ques_len)) * mask(ques_len, max_ques_len).reshape(n, R, max_ques_len),
+        "ques_length": ques_len,
+        "ans": tok((n, R, max_ans_len)) * mask(ans_len, max_ans_len).reshape(n, R, max_ans_len),
+        "ans_length": ans_len,
+        "cap": tok((n, max_cap_len)) * mask(cap_len, max_cap_len),
+        "cap_length": cap_len,
+        "opt_list": tok((m, max_ans_len)) * mask(opt_len, max_ans_len),
+        "opt_length": opt_len,
+        "opt": rng.integers(1, m + 1, size=(n, R, K)).astype(np.int32),           # prepro.py:151-160 (1-based)
+        "ans_index": rng.integers(1, K + 1, size=(n, R)).astype(np.int32),        # prepro.py:166-170
+        "num_rounds": np.full(n, R, dtype=np.int32),
+    }
+    if edge_cases and n >= 8:
+        out["opt"][0, 0, 0] = 2                                                   # the empty option is referenced
+        out["num_rounds"][5] = R - 1
+    if "im" in enc:
+        nimg = int(num_images or n)
+        out["img_pos"] = rng.permutation(nimg)[:n].astype(np.int32) if nimg >= n else \
+            rng.integers(0, nimg, size=n).astype(np.int32)
+        if "att" in enc:                                                          # pool5 as stored: N x C x S x S
+            S, Cc = int(params["imgSpatialSize"]), int(params["imgFeatureSize"])
+            out["images"] = np.maximum(rng.standard_normal((nimg, Cc, S, S), dtype=np.float32), 0) + 0.01
+        else:
+            out["images"] = np.maximum(rng.standard_normal((nimg, int(params["imgFeatureSize"])), dtype=np.float32), 0) + 0.01
+    return out
