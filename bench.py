@@ -264,8 +264,18 @@ def run_ours(args, rank, local, world):
     ms_dev, wall_dev, launches = timed(dev_loader, args.steps, 0 if args.ncu_range else 2)
     if args.ncu_range:
         eng.profiler_range(False)
-    stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS}
+    stats_shared = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS}
     ms_e2e, wall_e2e, _ = timed(host_loader, args.steps, 0)
+    # Roofline pass: in the timed region above the option-LSTM kernels share the GPU with the encoder's concurrent
+    # streams, so a CUDA-event bracket around one launch also contains the SM time it ceded.  The same K steps are
+    # therefore run once more on ONE timeline (reference order: encoder, then decoder) and the dominant kernel's launch
+    # duration is taken from there; the shared-machine figure is kept as `achieved_in_overlapped_step`.
+    eng.set_option_overlap(False)
+    model.trainIteration(dev_loader)
+    ms_iso, _, _ = timed(dev_loader, args.steps, 2)
+    stats = {k: eng.kernel_stats(k) for k in LSTM_STEP_KEYS}
+    eng.set_option_overlap(True)
+    model.trainIteration(dev_loader)
     # the same step fed by the HBM-resident corpus (dataloader.lua:324-478 on the device): per step
     # only the dialog indices cross PCIe.  Reported next to e2e, never instead of it.
     resident = None
@@ -274,18 +284,40 @@ def run_ours(args, rank, local, world):
         from visdial_b200.synthetic import make_corpus
         raw = make_corpus(p, num_threads=args.corpus_dialogs, num_opt_list=8000, seed=99 + rank)
         dl = Dataloader(eng, seed=7 + rank).initialize(dict(p, imgNorm=0, maxHistoryLen=60), ["train"], {"train": raw})
+        cpu_asm_us = None
+        if world == 1 and not args.no_cpu:      # CPU leg: the oracle's getTrainBatch indexing (numpy, host RAM) on the same corpus
+            from oracle.dataloader_oracle import DataloaderOracle
+            orc = DataloaderOracle(raw, use_history=True, concat_history=False, use_im=True, start=p["vocabSize"] - 1,
+                                   end=p["vocabSize"], img_norm=False, att=True)
+            rng = np.random.default_rng(0)
+            orc.get_batch(rng.integers(0, args.corpus_dialogs, size=args.batch), "disc", test_batch=False)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                orc.get_batch(rng.integers(0, args.corpus_dialogs, size=args.batch), "disc", test_batch=False)
+            cpu_asm_us = (time.perf_counter() - t0) / 20 * 1e6
+            del orc
         del raw
         for _ in range(2):
             model.trainIteration(dl)
         ms_res, wall_res, _ = timed(dl, args.steps, 0)
+        # batch assembly alone: device time of the two gather launches (CUDA events around each batch's launches) and
+        # the host-side cost of the call; bytes are summed over the batches actually drawn (trim widths vary)
         nb = 200
         eng.synchronize()
-        eng.timer_start()
+        eng.profile_reset()
+        eng.profile(1)
+        by = 0
+        t_host = time.perf_counter()
         for _ in range(nb):
             dl.getTrainBatch(p)
-        ms_asm = eng.timer_stop()
-        by, nl = dl.corpus["train"].batch_bytes()
-        resident = {"ms": max(ms_res, wall_res), "asm_us": ms_asm / nb * 1e3, "bytes": by, "launches": nl}
+            by += dl.corpus["train"].batch_bytes()[0]
+        t_host = (time.perf_counter() - t_host) / nb
+        eng.synchronize()
+        st = eng.kernel_stats("corpus_gather")
+        eng.profile(False)
+        nl = dl.corpus["train"].batch_bytes()[1]
+        resident = {"ms": max(ms_res, wall_res), "asm_us": st["ms"] / nb * 1e3, "bytes": by / nb, "launches": nl,
+                    "host_us": t_host * 1e6, "cpu_us": cpu_asm_us}
         dl.close()
     if rank == 0:
         sampler.mark_end()
@@ -316,7 +348,11 @@ def run_ours(args, rank, local, world):
     roofline = {"bound": "tensor", "kernel": "k_tc_gemm<256,LSTM_FWD|LSTM_BWD,2>: option-LSTM step (recurrent gate GEMM on tcgen05 + SeqLSTM pointwise epilogue), 19 fwd + 19 bwd launches per training step",
                 "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 operands)" % peaks["src"],
-                "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / max(ms_dev, 1e-9),
+                "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / max(ms_iso, 1e-9),
+                "measured_in": "a second pass of the same %d steps with the option stream serialised behind the encoder "
+                               "(%.3f ms/step), CUDA events around every launch of this kernel class" % (args.steps, ms_iso / args.steps),
+                "achieved_in_overlapped_step": (sum(stats_shared[k]["flops"] for k in LSTM_STEP_KEYS) /
+                                                max(sum(stats_shared[k]["ms"] for k in LSTM_STEP_KEYS) * 1e-3, 1e-12) / 1e12),
                 "algorithmic_flop_per_launch": fl / max(n_l, 1), "traffic": None}
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
@@ -344,9 +380,10 @@ def run_ours(args, rank, local, world):
             "unit": "QA-rounds/s", "h2d_bytes_per_step": 4 * args.batch, "d2h_bytes_per_step": 4,
             "what": "Model.trainIteration fed by visdial_b200.dataloader.Dataloader (corpus of %d dialogs resident in HBM, "
                     "batch gathered + trimmed on the device)" % args.corpus_dialogs,
-            "batch_assembly": {"us_per_batch": resident["asm_us"], "kernel_launches": resident["launches"],
-                               "algorithmic_bytes": resident["bytes"], "GB/s": gbs,
-                               "frac_of_hbm_peak": gbs / peaks["hbm"], "bound": "launch latency at B=%d" % args.batch}}
+            "batch_assembly": {"device_us_per_batch": resident["asm_us"], "host_us_per_call": resident["host_us"],
+                               "kernel_launches": resident["launches"], "algorithmic_bytes": resident["bytes"],
+                               "GB/s": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"], "bound": "hbm",
+                               "cpu_port_us_per_batch": resident["cpu_us"]}}
     if world == 1 and not args.no_cpu:
         threads = cpu_threads(args)
         sec, _ = cpu_oracle_step_time(args.cpu_batch, 1, 1, "reference", threads)

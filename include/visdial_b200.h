@@ -111,6 +111,12 @@ int vd_set_dropout_seed(vd_engine* e, uint64_t seed, uint64_t iteration);
 #define VD_MATH_TF32 0        /* dense contractions on tcgen05 tensor cores, TF32 operands, fp32 accumulate */
 #define VD_MATH_FP32 1        /* same contractions on CUDA cores in fp32 (verification mode) */
 int vd_set_math_mode(vd_engine* e, int32_t mode);
+/* Scheduling knob (results are identical either way).  on = 1 (default): the disc decoder's option LSTM (disc.lua:4-20),
+ * which does not depend on the encoder until the final dot product, runs on its own stream concurrently with the
+ * encoder's forward and backward, its persistent kernels leaving `reserve_sms` SMs (default 16, < 0 keeps the current
+ * value) to the encoder's chains.  on = 0: the reference's order (encoder, then decoder) on one timeline — used by
+ * bench.py to time the option-LSTM step kernel alone for the roofline. */
+int vd_set_option_overlap(vd_engine* e, int32_t on, int32_t reserve_sms);
 
 /* ---- fine-grained module protocol (what Model:forwardBackward calls, model.lua:297-337) ----- */
 int vd_encoder_forward(vd_engine* e, const vd_batch* b, const float** encOut_dev);       /* encoder:forward(inputs), :297 */

@@ -42,6 +42,18 @@ int vd_comm_unique_id(void* id_out);
 int vd_comm_init(vd_engine* e, const void* id, int32_t rank, int32_t world);
 int vd_memcpy_d2h(vd_engine* e, void* host_dst, const void* dev_src, size_t bytes);
 int vd_synchronize(vd_engine* e);
+/* dataloader on the device (dataloader.lua:143-478) */
+typedef struct vd_corpus vd_corpus;
+typedef struct vd_corpus_desc {
+  int32_t numThreads, numRounds, maxQuesLen, maxAnsLen, maxCapLen, numOptions, numOptList, numImages;
+  int32_t useHistory, concatHistory, useIm, maxHistoryLen, imgNorm, imgAtt, imgChannels, imgSpatial;
+  int32_t startToken, endToken;
+  const int32_t *ques, *ques_len, *ans, *ans_len, *cap, *cap_len, *opt, *opt_list, *opt_len, *ans_index, *img_pos, *num_rounds;
+  const float* images;
+} vd_corpus_desc;
+int vd_corpus_create(vd_engine* e, const vd_corpus_desc* d, vd_corpus** out);
+int vd_corpus_destroy(vd_corpus* c);
+int vd_corpus_get_batch(vd_corpus* c, const int64_t* inds, int32_t n, int32_t decoder_gen, vd_batch* out);
 ]]
 
 local M = {}

@@ -104,6 +104,7 @@ int vd_set_parameters(vd_engine* h, const float* src, int64_t n) {
 static void copy_out(Engine* e, float* dst, const float* src, int64_t n) {
   VD_REQUIRE(dst && n == e->nparams, VD_E_SHAPE, "n must equal vd_num_params");
   VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+  e->join_options_backward();
   VD_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->cx.stream));
   VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
 }
@@ -113,6 +114,7 @@ int vd_zero_grad(vd_engine* h) {
   VD_TRY({
     Engine* e = ENG(h);
     VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    e->join_options_backward();
     VD_CUDA_CHECK(cudaMemsetAsync(e->dW, 0, (size_t)e->nparams * sizeof(float), e->cx.stream));
   })
 }
@@ -122,6 +124,18 @@ int vd_set_training(vd_engine* h, int32_t training) {
 }
 int vd_set_dropout_seed(vd_engine* h, uint64_t seed, uint64_t iteration) {
   VD_TRY({ Engine* e = ENG(h); e->drop_seed = seed; e->drop_iter = iteration; })
+}
+int vd_set_option_overlap(vd_engine* h, int32_t on, int32_t reserve_sms) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    e->join_options_backward();
+    if (e->opt_fwd_pending) { VD_CUDA_CHECK(cudaStreamSynchronize(e->opt_stream)); e->opt_fwd_pending = false; }
+    e->opt_overlap = on != 0;
+    if (reserve_sms >= 0) {
+      VD_REQUIRE(reserve_sms <= e->cx.sm_count - 16, VD_E_BADARG, "reserve_sms leaves fewer than 16 SMs to the option stream");
+      e->opt_reserve_sms = reserve_sms & ~1;
+    }
+  })
 }
 int vd_set_math_mode(vd_engine* h, int32_t mode) {
   VD_TRY({ VD_REQUIRE(mode == VD_MATH_TF32 || mode == VD_MATH_FP32, VD_E_BADARG, "unknown math mode"); ENG(h)->math_mode = mode; })
@@ -224,7 +238,14 @@ int vd_device_alloc(vd_engine* h, void** ptr, size_t bytes) {
 int vd_device_free(vd_engine* h, void* ptr) {
   VD_TRY({ Engine* e = ENG(h); VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid)); if (ptr) VD_CUDA_CHECK(cudaFree(ptr)); })
 }
-int vd_synchronize(vd_engine* h) { VD_TRY({ VD_CUDA_CHECK(cudaStreamSynchronize(ENG(h)->cx.stream)); }) }
+int vd_synchronize(vd_engine* h) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    e->join_options_backward();
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+    if (e->opt_fwd_pending) VD_CUDA_CHECK(cudaStreamSynchronize(e->opt_stream));
+  })
+}
 int vd_stream(vd_engine* h, void** s) { VD_TRY({ NOTNULL(s); *s = (void*)ENG(h)->cx.stream; }) }
 int vd_timer_start(vd_engine* h) { VD_TRY({ Engine* e = ENG(h); VD_CUDA_CHECK(cudaEventRecord(e->t0, e->cx.stream)); }) }
 int vd_timer_stop(vd_engine* h, float* ms) {

@@ -75,6 +75,7 @@ void comm_destroy(Engine* e) {
 void Engine::allreduce_grads() {
   if (world <= 1) return;
   VD_REQUIRE(nccl_comm != nullptr, VD_E_STATE, "communicator not initialised");
+  join_options_backward();
   LaunchCtx::Scope sc(&cx, "allreduce", 0.0, 2.0 * 4.0 * (double)nparams);
   nccl_check(api().AllReduce(dW, dW, (size_t)nparams, ncclFloat32, ncclSum, (ncclComm_t)nccl_comm, cx.stream), "ncclAllReduce");
 }

@@ -144,13 +144,22 @@ Engine::Engine(const vd_params* p) {
   VD_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg.gpuid));
   VD_REQUIRE(prop.major == 10, VD_E_CUDA, "visdial_b200 is built for sm_100a (B200) only");
   cx.sm_count = prop.multiProcessorCount;
-  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+  // the encoder's chains of small dependent kernels get the highest priority, the option LSTM's SM-filling launches
+  // the lowest: a freed SM goes to the latency-bound chain first
+  int prio_lo = 0, prio_hi = 0;
+  VD_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&cx.stream, cudaStreamNonBlocking, prio_hi));
   main_stream = cx.stream;
-  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
-  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&main2_stream, cudaStreamNonBlocking));
-  VD_CUDA_CHECK(cudaStreamCreateWithFlags(&side2_stream, cudaStreamNonBlocking));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, prio_hi));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&main2_stream, cudaStreamNonBlocking, prio_hi));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&side2_stream, cudaStreamNonBlocking, prio_hi));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&opt_stream, cudaStreamNonBlocking, prio_lo));
   VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_opt_fork, cudaEventDisableTiming));
+  VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_opt_done, cudaEventDisableTiming));
+  if (const char* s = getenv("VD_OPT_OVERLAP")) opt_overlap = atoi(s) != 0;
+  if (const char* s = getenv("VD_OPT_RESERVE_SMS")) opt_reserve_sms = std::max(0, std::min(atoi(s), cx.sm_count - 16)) & ~1;
   size_t bytes = (size_t)nparams * sizeof(float);
   VD_CUDA_CHECK(cudaMalloc((void**)&W, bytes));
   VD_CUDA_CHECK(cudaMalloc((void**)&dW, bytes));
@@ -182,6 +191,7 @@ Engine::Engine(const vd_params* p) {
 Engine::~Engine() {
   cudaSetDevice(cfg.gpuid);
   cudaStreamSynchronize(cx.stream);
+  if (opt_stream) cudaStreamSynchronize(opt_stream);
   arena.release();
   for (auto& g : stage) g.release();
   cudaFree(W); cudaFree(dW); cudaFree(m); cudaFree(v); cudaFree(Wt); cudaFree(scalars_dev); cudaFree(segtab_dev);
@@ -195,6 +205,9 @@ Engine::~Engine() {
   if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
   if (main2_stream) { cudaStreamSynchronize(main2_stream); cudaStreamDestroy(main2_stream); }
   if (side2_stream) { cudaStreamSynchronize(side2_stream); cudaStreamDestroy(side2_stream); }
+  if (opt_stream) { cudaStreamSynchronize(opt_stream); cudaStreamDestroy(opt_stream); }
+  if (ev_opt_fork) cudaEventDestroy(ev_opt_fork);
+  if (ev_opt_done) cudaEventDestroy(ev_opt_done);
   for (auto e : ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(main_stream);
 }
@@ -482,7 +495,8 @@ void Engine::lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float*
     }
     gemm_atb(D, G, V1, Wp(0), cfg.E, nullptr, dP, G, dWs, G);
     colsum_add(cx, dWp(r.wseg + 1), dP, V1, G, G);
-    gemm_tn(V1, D, G, dP, G, nullptr, Ws, G, dWp(0), cfg.E, 1.f, nullptr, 0);
+    if (r.demb_out) gemm_tn(V1, D, G, dP, G, nullptr, Ws, G, r.demb_out, cfg.E, 0.f, nullptr, 0);   // folded in by the caller
+    else gemm_tn(V1, D, G, dP, G, nullptr, Ws, G, dWp(0), cfg.E, 1.f, nullptr, 0);
     VD_REQUIRE(dx_out == nullptr, VD_E_STATE, "projected-space embedding gradient: caller must not ask for dx");
     return;
   }
@@ -550,11 +564,16 @@ void Engine::encoder_forward(const vd_batch* b) {
   VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
   if (side_active) { cudaStreamSynchronize(side_stream); side_active = false; }   // only after an aborted call
   cx.stream = main_stream;
+  if (opt_fwd_pending || opt_bwd_pending) {       // a previous call sequence was abandoned half-way: drain before reuse
+    VD_CUDA_CHECK(cudaStreamSynchronize(opt_stream));
+    opt_fwd_pending = opt_bwd_pending = false;
+  }
   arena.reset();
   have_fwd = false;
   stage_batch(b);
   save_acts = training != 0;
   refresh_shadows();
+  if (opt_overlap && cfg.dec == DEC_DISC && db.options && db.To > 0) options_forward_async();
   conn_dh_l1 = conn_dc_l1 = conn_dc_l2 = nullptr;
   gen_h0[0] = gen_h0[1] = gen_c0[0] = gen_c0[1] = nullptr;
   const int E = cfg.E, H = cfg.H, R = cfg.R;
@@ -786,6 +805,7 @@ void Engine::encoder_backward(const float* dEnc) {
     }
   }
   join_side();
+  join_options_backward();
 }
 
 void Engine::fork_side() {
@@ -821,17 +841,49 @@ void Engine::forward_connect() {
   gen_h0[1] = encOut;
 }
 
+// disc.lua:4-20: the option LSTM over all N*100 candidate answers.  Depends only on the batch and the weights, so it
+// is enqueued on opt_stream before the encoder's kernels and meets the encoder output at disc_scores_fwd.
+void Engine::options_forward_async() {
+  const int64_t Ro = db.N * cfg.K;
+  cudaStream_t s = opt_overlap ? opt_stream : main_stream;
+  if (opt_overlap) {
+    VD_CUDA_CHECK(cudaEventRecord(ev_opt_fork, main_stream));          // batch staged, shadows refreshed
+    VD_CUDA_CHECK(cudaStreamWaitEvent(opt_stream, ev_opt_fork, 0));
+  }
+  cudaStream_t prev = cx.stream;
+  cx.stream = s;
+  if (opt_overlap) cx.sm_budget = cx.sm_count - opt_reserve_sms;   // leave SMs to the encoder's concurrent chains
+  ids_o = arena.get<int32_t>(Ro * db.To);
+  transpose_ids(cx, db.options, ids_o, Ro, db.To);
+  opt = make_run(db.To, Ro, cfg.E, cfg.H, seg("opt.lstm.weight"), nullptr, ids_o, nullptr);   // disc.lua:4-5: no maskzero
+  lstm_forward(opt, save_acts);
+  VD_CUDA_CHECK(cudaEventRecord(ev_opt_done, s));
+  cx.stream = prev;
+  cx.sm_budget = 0;
+  opt_fwd_pending = true;
+}
+
+void Engine::join_options_backward() {
+  if (!opt_bwd_pending) return;
+  opt_bwd_pending = false;
+  cudaStream_t prev = cx.stream;
+  cx.stream = main_stream;
+  VD_CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev_opt_done, 0));
+  if (opt_demb) add_inplace(cx, dWp(0), opt_demb, (int64_t)(cfg.V + 1) * cfg.E);
+  opt_demb = nullptr;
+  cx.stream = prev;
+}
+
 void Engine::decoder_forward() {
   VD_REQUIRE(have_fwd, VD_E_STATE, "decoder_forward before encoder_forward");
   const int E = cfg.E, H = cfg.H, K = cfg.K;
   const int64_t N = db.N;
   if (cfg.dec == DEC_DISC) {
     VD_REQUIRE(db.options && db.To > 0, VD_E_SHAPE, "disc decoder: options / To missing");
-    const int64_t Ro = N * K;
-    ids_o = arena.get<int32_t>(Ro * db.To);
-    transpose_ids(cx, db.options, ids_o, Ro, db.To);
-    opt = make_run(db.To, Ro, E, H, seg("opt.lstm.weight"), nullptr, ids_o, nullptr);   // disc.lua:4-5: no maskzero
-    lstm_forward(opt, save_acts);
+    if (!opt_fwd_pending) options_forward_async();          // normally started by encoder_forward already
+    VD_CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev_opt_done, 0));
+    opt_fwd_pending = false;
+    cx.stream = main_stream;
     scores = arena.get<float>(N * K);
     disc_scores_fwd(cx, opt.h_last(), encOut, scores, N, K, H);
   } else {
@@ -897,12 +949,30 @@ void Engine::decoder_backward() {
     const int64_t Ro = N * K;
     float* dfeat = arena.get<float>(Ro * H);
     disc_scores_bwd(cx, dscores, opt.h_last(), encOut, dfeat, dEncFromDec, N, K, H);
+    // The option BPTT feeds only opt.lstm's weights and the word embedding: it runs on opt_stream while the caller
+    // goes on to the encoder's backward; join_options_backward() (encoder_backward / any gradient consumer) waits.
+    cudaStream_t prev = cx.stream;
+    if (opt_overlap) {
+      VD_CUDA_CHECK(cudaEventRecord(ev_opt_fork, cx.stream));
+      VD_CUDA_CHECK(cudaStreamWaitEvent(opt_stream, ev_opt_fork, 0));
+      cx.stream = opt_stream;
+      cx.sm_budget = cx.sm_count - opt_reserve_sms;
+    }
     if (math_mode == VD_MATH_TF32) {
-      lstm_backward(opt, nullptr, dfeat, nullptr, nullptr, nullptr, nullptr);   // embedding gradient in projected space
+      // embedding gradient in projected space; written to a private (V+1,E) buffer when overlapped, because the
+      // encoder's embedding gradients accumulate into dW(wordEmbed) with atomics at the same time
+      opt.demb_out = opt_overlap ? (opt_demb = arena.get<float>((int64_t)(cfg.V + 1) * E)) : nullptr;
+      lstm_backward(opt, nullptr, dfeat, nullptr, nullptr, nullptr, nullptr);
     } else {
       float* dx = arena.get<float>(Ro * db.To * E);
       lstm_backward(opt, nullptr, dfeat, nullptr, dx, nullptr, nullptr);
-      embed_scatter_add(cx, dWp(0), dx, E, ids_o, Ro * db.To, E, dropcfg(0.f), 0);
+      embed_scatter_add(cx, dWp(0), dx, E, ids_o, Ro * db.To, E, dropcfg(0.f), 0);   // atomics: safe next to the encoder's
+    }
+    if (opt_overlap) {
+      VD_CUDA_CHECK(cudaEventRecord(ev_opt_done, opt_stream));
+      cx.stream = prev;
+      cx.sm_budget = 0;
+      opt_bwd_pending = true;
     }
   } else {
     VD_REQUIRE(dlogits, VD_E_STATE, "decoder_backward before criterion_backward");
@@ -986,6 +1056,7 @@ void Engine::gen_option_lhood() {
 // model.lua:96-99 + optim_updates.lua:62-91
 void Engine::clamp_adam_step(float lr) {
   VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  join_options_backward();
   float gscale = 1.f;
   if (world > 1) {
     allreduce_grads();

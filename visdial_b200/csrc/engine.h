@@ -55,6 +55,7 @@ struct LstmRun {
   const float* h0 = nullptr; const float* c0 = nullptr;
   float* h = nullptr; float* c = nullptr; float* gates = nullptr;
   bool saved = false;
+  float* demb_out = nullptr;         // projected-space embedding gradient goes here (overwritten) instead of dW(wordEmbed) +=
   // forward run state (lstm_forward_begin / _step)
   bool tc = false;                   // fused tcgen05 step kernels
   bool step_xproj = false;           // dense input projected per step (layer-2 of a pipelined pair) instead of batched
@@ -163,6 +164,16 @@ struct Engine {
   void lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2, const float* dc_last2, const float* dh_last1,
                           const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb);
   cudaStream_t main2_stream = nullptr, side2_stream = nullptr;
+  // The disc decoder's option LSTM (disc.lua:4-20) does not depend on the encoder until the final dot product, and its
+  // BPTT does not feed the encoder's: both run on their own low-priority stream, concurrently with the encoder's
+  // latency-bound chains (which keep priority for SMs as they free up).
+  cudaStream_t opt_stream = nullptr;
+  cudaEvent_t ev_opt_fork = nullptr, ev_opt_done = nullptr;
+  bool opt_overlap = true, opt_fwd_pending = false, opt_bwd_pending = false;
+  int opt_reserve_sms = 16;         // SMs the option stream's persistent kernels leave free while they overlap the encoder
+  float* opt_demb = nullptr;
+  void options_forward_async();
+  void join_options_backward();      // main stream waits for the option BPTT and folds its embedding gradient in
   std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t pool_event(size_t i);
   void lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last, const float* dc_last, float* dx_out,

@@ -845,12 +845,12 @@ static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, 
     attr_set = true;
   }
   if (CG == 1) {
-    int grid = std::min(num_tiles, cx.sm_count);
+    int grid = std::min(num_tiles, cx.sms());
     k_tc_gemm<BN, MODE, 1><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, em, p);
   } else {
     // CTA pairs: a 2-CTA cluster per 256-row tile, one pair per TPC (num_tiles counts 256-row tiles here)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * std::min(num_tiles, cx.sm_count / 2));
+    cfg.gridDim = dim3(2 * std::min(num_tiles, cx.sms() / 2));
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = cx.stream;
@@ -904,7 +904,10 @@ bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t
   if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
   const int tiles = cdiv(M, BM) * cdiv(N, ATB_BN);
   // whole waves: the largest split count with tiles * splits <= 2 * #SM (one CTA per SM at this smem footprint)
-  int64_t splits = std::max<int64_t>(1, std::min<int64_t>((2LL * cx.sm_count) / tiles, K / (ATB_KB * 4)));
+  // (under an SM budget — the option stream sharing the GPU with the encoder's chains — a single wave of budget CTAs, so
+  // that the reserved SMs really stay free: a second wave would be placed on them)
+  const int64_t cta_cap = cx.sm_budget > 0 ? cx.sm_budget : 2LL * cx.sm_count;
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cta_cap / tiles, K / (ATB_KB * 4)));
   int64_t kps = ((K + splits - 1) / splits + ATB_KB - 1) / ATB_KB * ATB_KB;
   splits = (K + kps - 1) / kps;
   AtbParams p = {M, N, K, kps, C, ldc};

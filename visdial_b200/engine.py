@@ -248,6 +248,9 @@ class Engine:
     def set_math_mode(self, mode: int):
         check(self.lib.vd_set_math_mode(self.h, mode))
 
+    def set_option_overlap(self, on: bool, reserve_sms: int = -1):
+        check(self.lib.vd_set_option_overlap(self.h, int(on), int(reserve_sms)))
+
     # ---- module protocol -----------------------------------------------------------------------
     def _N(self, batch: Batch) -> int:
         return batch.c.B * self.params["maxQuesCount"]
