@@ -844,13 +844,21 @@ static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, 
     VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
+  // Persistent grid, balanced waves: with pmax CTAs (pairs) available the tiles need ceil(tiles/pmax) rounds; the
+  // smallest grid that still finishes in that many rounds is used, so no CTA idles through a ragged last round and the
+  // SMs not needed stay free for concurrent streams (250 backward tiles: 63 pairs x 4 rounds instead of 74 x 3.4).
+  auto balanced = [&](int pmax) {
+    if (num_tiles <= pmax) return num_tiles;
+    const int rounds = cdiv(num_tiles, pmax);
+    return cdiv(num_tiles, rounds);
+  };
   if (CG == 1) {
-    int grid = std::min(num_tiles, cx.sms());
+    int grid = balanced(cx.sms());
     k_tc_gemm<BN, MODE, 1><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, em, p);
   } else {
     // CTA pairs: a 2-CTA cluster per 256-row tile, one pair per TPC (num_tiles counts 256-row tiles here)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * std::min(num_tiles, cx.sms() / 2));
+    cfg.gridDim = dim3(2 * balanced(cx.sms() / 2));
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = cx.stream;
@@ -861,6 +869,12 @@ static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, 
     VD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, MODE, 2>, tA, tB, em, p));
   }
   check_launch(cx, "k_tc_gemm");
+}
+
+static int small_narrow() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VD_SMALL_NARROW"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 static bool use_cta_pairs() {
@@ -949,6 +963,9 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
       launch<256, MODE_LSTM_FWD, 2>(cx, tA, tB, p, cdiv(R, 2 * BM) * (H / 64), &em);
     }
     else launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
+  } else if (small_narrow() == 2) {          // experiment: few fat CTAs (64 hidden units per tile)
+    CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 64);
+    launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
   } else {                                   // few rows (encoder LSTMs): 16 hidden units per tile, 4x the CTAs
     CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 16);
     launch<64, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 16));
@@ -991,6 +1008,9 @@ bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, con
       em.h = em.c;
       launch<128, MODE_LSTM_BWD, 2>(cx, tA, tB64, p, cdiv(R, 2 * BM) * (H / 128), &em);
     } else launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
+  } else if (small_narrow() >= 1) {          // experiment: 128 hidden units per tile
+    CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 128);
+    launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
   } else {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 32);
     launch<32, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
