@@ -753,9 +753,17 @@ __global__ void k_fill(float* __restrict__ buf, int64_t n, float val) {
 }
 
 // ---- rows grouped by token id (counting sort) + segmented row sum ---------------------------------------
-__global__ void k_tok_hist(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ counts) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(counts + ids[i], 1);
+// Half of the option tokens are the pad id 0 and a handful of words are very frequent, so one atomic per element
+// serialises on a few addresses.  Pad ids are counted per block (one atomic per block); every other id is aggregated
+// per warp with match.any (one atomic per distinct id per warp).
+__global__ void __launch_bounds__(256) k_tok_hist(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int v = i < n ? ids[i] : -1;
+  const int nz = __syncthreads_count(v == 0);
+  if (threadIdx.x == 0 && nz) atomicAdd(counts, nz);
+  const unsigned peers = __match_any_sync(0xffffffffu, v > 0 ? v : -1 - lane);
+  if (v > 0 && lane == __ffs(peers) - 1) atomicAdd(counts + v, __popc(peers));
 }
 // single block: offsets[v] = exclusive prefix sum of counts[v]; cursor[v] = offsets[v]
 __global__ void k_tok_scan(const int32_t* __restrict__ counts, int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int nv) {
@@ -773,12 +781,32 @@ __global__ void k_tok_scan(const int32_t* __restrict__ counts, int32_t* __restri
 }
 __global__ void k_tok_fill(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
                            int32_t* __restrict__ sorted_tok) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int v = ids[i];
-  int pos = atomicAdd(cursor + v, 1);
-  perm[pos] = (int32_t)i;
-  sorted_tok[pos] = v;
+  __shared__ int warp_z[8];
+  __shared__ int block_base;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = i < n ? ids[i] : -1;
+  // pad ids: rank inside the block from ballots, one cursor atomic per block
+  const unsigned zb = __ballot_sync(0xffffffffu, v == 0);
+  if (lane == 0) warp_z[warp] = __popc(zb);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) { int c = warp_z[w]; warp_z[w] = tot; tot += c; }
+    block_base = tot ? atomicAdd(cursor, tot) : 0;
+  }
+  __syncthreads();
+  // other ids: one cursor atomic per distinct id per warp
+  const unsigned peers = __match_any_sync(0xffffffffu, v > 0 ? v : -1 - lane);
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (v > 0 && lane == leader) base = atomicAdd(cursor + v, __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  const unsigned lt = (1u << lane) - 1u;
+  int pos = -1;
+  if (v == 0) pos = block_base + warp_z[warp] + __popc(zb & lt);
+  else if (v > 0) pos = base + __popc(peers & lt);
+  if (pos >= 0) { perm[pos] = (int32_t)i; sorted_tok[pos] = v; }
 }
 // Each block owns SEG_ROWS consecutive positions of the token-sorted row list; it streams those rows (ncols floats
 // each, coalesced) and flushes a running sum into out[token] whenever the token changes.  Balanced by construction.
