@@ -389,8 +389,16 @@ cudaEvent_t Engine::pool_event(size_t i) {
 
 // Wavefront over two stacked layers: layer-2 step t only needs layer-1 step t, so the two recurrences run one step
 // apart on two streams instead of back to back (the per-step kernels of these 320-row LSTMs are latency-bound).
+// Below this many rows the per-step contractions leave the tensor-core path (M < 64) and the two-stream wavefront only
+// adds launches and event traffic.
+static int64_t wavefront_min_rows() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("VD_WAVEFRONT_MIN_ROWS"); v = e ? atoll(e) : 64; }
+  return v;
+}
+
 void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb) {
-  const bool pipelined = math_mode == VD_MATH_TF32 && l2.H % 64 == 0 && sb != nullptr && sb != sa;
+  const bool pipelined = math_mode == VD_MATH_TF32 && l2.H % 64 == 0 && sb != nullptr && sb != sa && l2.R >= wavefront_min_rows();
   cx.stream = sa;
   if (!pipelined) {
     lstm_forward(l1, true);
@@ -519,7 +527,7 @@ void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2,
   const int H = l2.H, G = 4 * l2.H;
   const int64_t R = l2.R;
   float* dx2 = arena.get<float>((int64_t)l2.T * R * l2.D);      // = gradient wrt layer-1 outputs, all steps
-  const bool pipelined = math_mode == VD_MATH_TF32 && H % 128 == 0 && sb != nullptr && sb != sa;
+  const bool pipelined = math_mode == VD_MATH_TF32 && H % 128 == 0 && sb != nullptr && sb != sa && R >= wavefront_min_rows();
   cx.stream = sa;
   if (!pipelined) {
     lstm_backward(l2, nullptr, dh_last2, dc_last2, dx2, nullptr, nullptr);
