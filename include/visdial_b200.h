@@ -98,6 +98,9 @@ const char* vd_last_error(void);
 int vd_num_params(vd_engine* e, int64_t* n);
 int vd_param_buffers(vd_engine* e, float** W_dev, float** dW_dev);
 int vd_optim_buffers(vd_engine* e, float** m_dev, float** v_dev, int64_t* t);
+/* restore Adam's state table (optims.m / .v / .t of model_utils/optim_updates.lua:67-84) from HOST vectors of
+ * vd_num_params floats — resuming from a checkpoint written by train.lua:99-102 */
+int vd_set_optim_state(vd_engine* e, const float* m_host, const float* v_host, int64_t t);
 int vd_set_parameters(vd_engine* e, const float* host_src, int64_t n);   /* wrapperW:copy(modelW), evaluate.lua:91 */
 int vd_get_parameters(vd_engine* e, float* host_dst, int64_t n);
 int vd_get_gradients(vd_engine* e, float* host_dst, int64_t n);

@@ -243,3 +243,46 @@ def test_errors_are_loud():
     with pytest.raises(VdError):                       # no backward from an eval-mode forward
         eng.criterion_backward(Batch(nb)) or eng.decoder_backward(Batch(nb))
     eng.close()
+
+
+def test_checkpoint_round_trip_resumes_training(tmp_path):
+    """train.lua:99-102 / :33-34,78-80: a model restored from the .t7 checkpoint (weights, learning rate, Adam state)
+    continues exactly like the one that wrote it; the model_final.t7 form carries float weights only."""
+    from visdial_b200 import t7
+    p = small_params("mn-att-ques-im-hist", "disc", batchSize=3)
+
+    class DL:
+        def __init__(self): self.i = 0
+        def getTrainBatch(self, params):
+            self.i += 1
+            return small_batch(params, B=3, seed=40 + self.i)
+
+    a = Model(p, seed=3)
+    a.engine.set_math_mode(VD_MATH_FP32)
+    dl = DL()
+    for _ in range(2):
+        a.trainIteration(dl)
+    path = str(tmp_path / "model_epoch_1.t7")
+    a.save(path)
+    a.save(str(tmp_path / "model_final.t7"), final=True)
+
+    raw = t7.load(path)
+    assert set(raw) == {"modelW", "optims", "modelParams", "layout"} and raw["optims"]["t"] == 2
+    assert raw["modelParams"]["encoder"] == "mn-att-ques-im-hist"
+    final = t7.load(str(tmp_path / "model_final.t7"))
+    assert "optims" not in final and np.array_equal(final["modelW"], raw["modelW"])
+
+    b = Model(raw["modelParams"] | {"gpuid": 0}, seed=99)                 # evaluate.lua:61-91: params come from the file
+    b.engine.set_math_mode(VD_MATH_FP32)
+    b.load(path, restore_adam_state=True)
+    b.iteration = a.iteration
+    assert b.optims["learningRate"] == a.optims["learningRate"]
+    np.testing.assert_array_equal(b.engine.get_parameters(), a.engine.get_parameters())
+    dl_b = DL(); dl_b.i = dl.i
+    la, lb = a.trainIteration(dl), b.trainIteration(dl_b)
+    assert abs(la - lb) <= 1e-6 * max(1.0, abs(la))
+    np.testing.assert_allclose(b.engine.get_parameters(), a.engine.get_parameters(), rtol=0, atol=2.1e-3)
+    assert float(np.abs(b.engine.get_parameters() - a.engine.get_parameters()).mean()) < 1e-6
+    with pytest.raises(Exception):
+        Model(small_params("lf-ques", "gen"), seed=1).load(path)           # parameter count mismatch is an error
+    a.engine.close(); b.engine.close()

@@ -66,6 +66,7 @@ SIGNATURES = {
     "vd_num_params": [_H, _P(C.c_int64)],
     "vd_param_buffers": [_H, _P(C.c_void_p), _P(C.c_void_p)],
     "vd_optim_buffers": [_H, _P(C.c_void_p), _P(C.c_void_p), _P(C.c_int64)],
+    "vd_set_optim_state": [_H, C.c_void_p, C.c_void_p, C.c_int64],
     "vd_set_parameters": [_H, C.c_void_p, C.c_int64],
     "vd_get_parameters": [_H, C.c_void_p, C.c_int64],
     "vd_get_gradients": [_H, C.c_void_p, C.c_int64],

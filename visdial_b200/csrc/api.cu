@@ -92,6 +92,18 @@ int vd_param_buffers(vd_engine* h, float** W, float** dW) {
 int vd_optim_buffers(vd_engine* h, float** m, float** v, int64_t* t) {
   VD_TRY({ Engine* e = ENG(h); if (m) *m = e->m; if (v) *v = e->v; if (t) *t = e->adam_t; })
 }
+int vd_set_optim_state(vd_engine* h, const float* m_host, const float* v_host, int64_t t) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(m_host && v_host && t >= 0, VD_E_BADARG, "vd_set_optim_state: m / v null or t < 0");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    const size_t bytes = (size_t)e->nparams * sizeof(float);
+    VD_CUDA_CHECK(cudaMemcpyAsync(e->m, m_host, bytes, cudaMemcpyHostToDevice, e->cx.stream));
+    VD_CUDA_CHECK(cudaMemcpyAsync(e->v, v_host, bytes, cudaMemcpyHostToDevice, e->cx.stream));
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+    e->adam_t = t;
+  })
+}
 int vd_set_parameters(vd_engine* h, const float* src, int64_t n) {
   VD_TRY({
     Engine* e = ENG(h);

@@ -235,6 +235,13 @@ class Engine:
         return (DeviceTensor(self, m.value, (self.num_params,)).numpy(),
                 DeviceTensor(self, v.value, (self.num_params,)).numpy(), t.value)
 
+    def set_optim_state(self, m: np.ndarray, v: np.ndarray, t: int):
+        m = np.ascontiguousarray(m, dtype=np.float32)
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        if m.size != self.num_params or v.size != self.num_params:
+            raise ValueError("Adam state must have vd_num_params elements")
+        check(self.lib.vd_set_optim_state(self.h, m.ctypes.data, v.ctypes.data, int(t)))
+
     def zero_grad(self):
         check(self.lib.vd_zero_grad(self.h))
 

@@ -127,3 +127,16 @@ class Model:
             ranks.append(self.retrieveBatch(batch).reshape(-1, self.params["maxQuesCount"]))
         self.wrapper.training()
         return np.concatenate(ranks, 0)
+
+    # ---- checkpoints (train.lua:33-34,78-80,99-102,120-121; evaluate.lua:58-91) -------------------------------
+    def save(self, path: str, final: bool = False):
+        """torch.save(path, {modelW, optims, modelParams}) — `final` = the model_final.t7 form (float weights, no optims)."""
+        from .checkpoint import save_checkpoint
+        save_checkpoint(self, path, final)
+
+    def load(self, path: str, permutation=None, restore_adam_state: bool = False):
+        """wrapperW:copy(savedModel.modelW); optims.learningRate = savedModel.optims.learningRate."""
+        from .checkpoint import load_checkpoint, restore
+        ck = load_checkpoint(path, permutation)
+        restore(self, ck, restore_adam_state)
+        return ck
