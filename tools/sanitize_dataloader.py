@@ -18,10 +18,18 @@ raw = make_corpus(p, 24, 120, seed=1, ques_len_cap=14 if concat else None, ans_l
 m = Model(p, seed=2)
 opt = dict(p, useHistory="hist" in enc, concatHistory=concat, useIm="im" in enc, maxHistoryLen=60, imgNorm=1)
 dl = Dataloader(m.engine, seed=3).initialize(opt, ["train", "val"], {"train": raw, "val": raw})
-for _ in range(2):
-    print("loss", m.trainIteration(dl))
+train = "--no-train" not in sys.argv
+if train:
+    for _ in range(2):
+        print("loss", m.trainIteration(dl))
 b, nxt = dl.getTestBatch(0, p, "val")
-print("ranks", m.retrieveBatch(b)[:10])
+if train:
+    print("ranks", m.retrieveBatch(b)[:10])
+else:                                   # dataloader kernels only: every batch form, read back
+    for mode in (0, 1, 2):
+        d = dl.corpus["train"].get_batch(np.array([0, 5, 5, 23, 7]), mode)
+        print(mode, {k: v.shape for k, v in d.numpy().items()})
+    print({k: dl.corpus["val"].read(k).shape for k in ("ques_fwd", "hist", "ans_in", "opt_out", "img_fv")})
 m.engine.synchronize()
 dl.close()
 m.engine.close()
