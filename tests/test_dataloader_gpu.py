@@ -161,3 +161,56 @@ def test_training_from_device_batches_equals_host_batches(enc, dec):
         assert abs(a - b) <= 1e-5 * max(1.0, abs(b))
     d = np.abs(losses[0][3] - losses[1][3])
     assert d.max() <= 7e-3 and (d > 1e-5).mean() < 1e-3
+
+
+# ---- committed fixtures: the device path against tests/golden/dataloader/*.npz, no oracle in the loop ------------
+import glob
+import os
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataloader", "*.npz")))
+GOLD_INDS = np.array([0, 1, 3, 4, 5, 5, 11])
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(g)[:-4] for g in GOLD])
+def test_device_dataloader_reproduces_golden(path):
+    enc, dec = os.path.basename(path)[:-4].split("__")
+    z = np.load(path)
+    params = small_params(enc, dec)
+    raw = {k[4:]: z[k] for k in z.files if k.startswith("raw_")}
+    eng = Engine(params)
+    dl = Dataloader(eng).initialize(_opt(params, True), ["train"], {"train": raw})
+    c = dl.corpus["train"]
+    for k in z.files:
+        if not k.startswith("prep_"):
+            continue
+        got = c.read(k[5:]).reshape(z[k].shape)
+        if z[k].dtype.kind == "f":
+            np.testing.assert_allclose(got, z[k], rtol=1e-6, atol=1e-7, err_msg=k)
+        else:
+            assert np.array_equal(got, z[k]), k
+    for tag, mode in (("train", 0 if dec == "disc" else 1), ("test", 0 if dec == "disc" else 2)):
+        ref = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + "_") and k != tag + "_num_rounds"}
+        _same_batch(c.get_batch(GOLD_INDS, mode), ref)
+    dl.close(); eng.close()
+
+
+@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("lf-ques-im-hist", "gen")])
+def test_model_retrieve_over_the_device_dataloader(enc, dec):
+    """Model:retrieve (model.lua:142-189) walking a split through getTestBatch: ranks from device-assembled batches ==
+    ranks from the oracle's host batches, exactly (forward-only path, no atomics)."""
+    params, raw, orc, eng, dl = _setup(enc, dec, n=20)
+    eng.close()
+    p = dict(params, batchSize=8)
+    model = Model(p, seed=4)
+    model.engine.set_math_mode(1)
+    d2 = Dataloader(model.engine).initialize(_opt(params, True), ["val"], {"val": raw})
+    got = model.retrieve(d2, "val")
+
+    class HostLoader:
+        numThreads = {"val": 20}
+        def getTestBatch(self, start, pp, dtype):
+            nxt = min(20, start + pp["batchSize"])
+            return orc.get_batch(np.arange(start, nxt), dec, test_batch=True), nxt
+    want = model.retrieve(HostLoader(), "val")
+    assert got.shape == (20, 10) and np.array_equal(got, want)
+    d2.close(); model.engine.close()

@@ -108,3 +108,30 @@ def test_attention_features_are_permuted_after_normalising():
     assert x.shape == (8, 3, 3, 8)
     assert np.allclose(np.linalg.norm(x, axis=3), 1, atol=1e-5)   # sum over dim 2 of N x C x S x S = channel norm
     assert np.allclose(x[2, 1, 2] * np.linalg.norm(raw["images"][2, :, 1, 2]), raw["images"][2, :, 1, 2], atol=1e-5)
+
+
+# ---- committed fixtures (tests/golden/dataloader/*.npz, made by tests/golden/make_golden_dataloader.py) ----------
+import glob
+import os
+import sys
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataloader", "*.npz")))
+
+
+def test_dataloader_fixtures_exist():
+    assert len(GOLD) == 4
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(g)[:-4] for g in GOLD])
+def test_oracle_reproduces_dataloader_golden(path):
+    sys.path.insert(0, os.path.join(os.path.dirname(path), ".."))
+    from make_golden_dataloader import build
+    enc, dec = os.path.basename(path)[:-4].split("__")
+    _, out = build(enc, dec)
+    z = np.load(path)
+    assert sorted(z.files) == sorted(out)
+    for k in z.files:
+        if z[k].dtype.kind == "f":
+            np.testing.assert_allclose(out[k], z[k], rtol=1e-6, atol=1e-7, err_msg=k)
+        else:
+            assert np.array_equal(out[k], z[k]), k
