@@ -33,6 +33,33 @@ def test_python_binding_covers_the_header():
     assert declared == bound, declared ^ bound
 
 
+def _struct_fields(name):
+    """field names of `typedef struct <name> { ... } <name>;` in declaration order"""
+    src = open(os.path.join(ROOT, "include", "visdial_b200.h")).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split(None, 2)[2]
+        out += [n.strip().lstrip("*") for n in names.split(",")]
+    return out
+
+
+@pytest.mark.parametrize("name,cls", [("vd_params", _lib.vd_params), ("vd_batch", _lib.vd_batch),
+                                      ("vd_corpus_desc", _lib.vd_corpus_desc)])
+def test_ctypes_structs_mirror_the_header(name, cls):
+    assert [f[0] for f in cls._fields_] == _struct_fields(name)
+
+
+def test_corpus_desc_layout_is_the_c_layout():
+    # 18 int32 (72 bytes, already 8-aligned) followed by 13 pointers
+    assert C.sizeof(_lib.vd_corpus_desc) == 72 + 13 * 8
+    assert _lib.vd_corpus_desc.ques.offset == 72 and _lib.vd_corpus_desc.images.offset == 72 + 12 * 8
+
+
 def test_no_torch_types_in_abi_and_static_cudart():
     src = open(os.path.join(ROOT, "include", "visdial_b200.h")).read()
     assert "torch" not in src.lower().replace("torch7", "").replace("torch.", "") or True
