@@ -214,3 +214,25 @@ def test_model_retrieve_over_the_device_dataloader(enc, dec):
     want = model.retrieve(HostLoader(), "val")
     assert got.shape == (20, 10) and np.array_equal(got, want)
     d2.close(); model.engine.close()
+
+
+def test_initialize_from_files(tmp_path):
+    """dataloader:initialize's file half (dataloader.lua:13-129): visdial_params.json + visdial_data.h5 + data_img.h5
+    named as prepro.py / prepro_img_*.lua name them -> the same batches as the in-memory path."""
+    import json
+    from visdial_b200 import h5lite
+    params, raw, orc, eng, dl = _setup("mn-att-ques-im-hist", "disc", n=16)
+    dl.close()
+    V = params["vocabSize"]
+    h5lite.write(str(tmp_path / "visdial_data.h5"),
+                 {k + "_val": np.asarray(v, np.uint32) for k, v in raw.items() if k != "images"})       # prepro.py:267-277
+    h5lite.write(str(tmp_path / "data_img.h5"), {"images_val": raw["images"]})
+    json.dump({"word2ind": {"w%d" % i: i for i in range(1, V - 1)}, "ind2word": {}, "unique_img_val": []},
+              open(str(tmp_path / "visdial_params.json"), "w"))
+    opt = dict(_opt(params, True), inputJson=str(tmp_path / "visdial_params.json"),
+               inputQues=str(tmp_path / "visdial_data.h5"), inputImg=str(tmp_path / "data_img.h5"))
+    d2 = Dataloader(eng).initialize_from_files(opt, ["val"])
+    assert d2.vocabSize == V and d2.word2ind["<START>"] == V - 1 and d2.word2ind["<END>"] == V and d2.word2ind["w3"] == 3
+    inds = np.array([1, 4, 4, 15])
+    _same_batch(d2.corpus["val"].get_batch(inds, 0), orc.get_batch(inds, "disc", test_batch=True))
+    d2.close(); eng.close()

@@ -176,7 +176,10 @@ class Dataloader:
             self.vocabSize = vocab_size_no_specials + 2                             # :17-22
         else:
             self.vocabSize = int(opt["vocabSize"])
-        self.word2ind = {"<START>": self.vocabSize - 1, "<END>": self.vocabSize}
+        w2i = dict(getattr(self, "word2ind", None) or {})                           # the json's words, when read from files
+        w2i["<START>"], w2i["<END>"] = self.vocabSize - 1, self.vocabSize           # :17-22
+        self.word2ind = w2i
+        self.ind2word = {v: k for k, v in w2i.items()}                              # :24-29
         self.useHistory, self.concatHistory, self.useIm = bool(opt.get("useHistory")), bool(opt.get("concatHistory")), bool(opt.get("useIm"))
         self.maxHistoryLen = int(opt.get("maxHistoryLen") or 60)                    # :142
         for dtype in subsets:
@@ -196,6 +199,30 @@ class Dataloader:
         if self.concatHistory:
             self.maxHistoryLen = min(self.maxQuesCount * (self.maxQuesLen + self.maxAnsLen), 300)   # :217
         return self
+
+    def initialize_from_files(self, opt: dict, subsets):
+        """The file-reading half of dataloader:initialize (dataloader.lua:13-129): `opt.inputJson` (word2ind ...),
+        `opt.inputQues` (visdial_data.h5) and, when the encoder uses the image, `opt.inputImg` (data_img.h5), read with
+        visdial_b200.h5lite (no h5py / libhdf5 in this image; DESIGN.md §13 for what that reader covers)."""
+        import json
+        from . import h5lite
+        info = json.load(open(opt["inputJson"]))                                    # :13-15
+        for k, v in info.items():
+            setattr(self, k, v)
+        n_words = len(info["word2ind"])                                             # :17-22
+        ques = h5lite.read(opt["inputQues"])                                        # :33-34
+        imgs = h5lite.read(opt["inputImg"]) if opt.get("useIm") else {}             # :36-37
+        data = {}
+        for dtype in subsets:
+            d = h5lite.split(ques, dtype)                                           # :45-57,108-129
+            if not d:
+                raise ValueError("no '%s' datasets in %s" % (dtype, opt["inputQues"]))
+            if opt.get("useIm"):
+                if "images_" + dtype not in imgs:
+                    raise ValueError("no 'images_%s' in %s" % (dtype, opt["inputImg"]))
+                d["images"] = imgs["images_" + dtype]                               # :61
+            data[dtype] = d
+        return self.initialize(dict(opt, vocabSize=n_words + 2), subsets, data, vocab_size_no_specials=n_words)
 
     def getTrainBatch(self, params: dict, batchSize: int = None) -> DeviceBatch:
         size = int(batchSize or params["batchSize"])                                # :325
