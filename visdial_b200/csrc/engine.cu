@@ -153,6 +153,8 @@ Engine::Engine(const vd_params* p) {
   VD_CUDA_CHECK(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, prio_hi));
   VD_CUDA_CHECK(cudaStreamCreateWithPriority(&main2_stream, cudaStreamNonBlocking, prio_hi));
   VD_CUDA_CHECK(cudaStreamCreateWithPriority(&side2_stream, cudaStreamNonBlocking, prio_hi));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&main3_stream, cudaStreamNonBlocking, prio_hi));
+  VD_CUDA_CHECK(cudaStreamCreateWithPriority(&side3_stream, cudaStreamNonBlocking, prio_hi));
   VD_CUDA_CHECK(cudaStreamCreateWithPriority(&opt_stream, cudaStreamNonBlocking, prio_lo));
   VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -205,6 +207,8 @@ Engine::~Engine() {
   if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
   if (main2_stream) { cudaStreamSynchronize(main2_stream); cudaStreamDestroy(main2_stream); }
   if (side2_stream) { cudaStreamSynchronize(side2_stream); cudaStreamDestroy(side2_stream); }
+  if (main3_stream) { cudaStreamSynchronize(main3_stream); cudaStreamDestroy(main3_stream); }
+  if (side3_stream) { cudaStreamSynchronize(side3_stream); cudaStreamDestroy(side3_stream); }
   if (opt_stream) { cudaStreamSynchronize(opt_stream); cudaStreamDestroy(opt_stream); }
   if (ev_opt_fork) cudaEventDestroy(ev_opt_fork);
   if (ev_opt_done) cudaEventDestroy(ev_opt_done);
@@ -351,7 +355,8 @@ void Engine::lstm_forward_step(LstmRun& r, int t) {
     const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
     int has_x = 0;
     if (!r.ptable) {
-      if (per_step_x) gemm_tn((int)R, G, D, r.x + (int64_t)t * R * D, lda, nullptr, WtS, D + H, g, G, 0.f, xbias, 0);
+      if (per_step_x && !r.xproj_external)
+        gemm_tn((int)R, G, D, r.x + (int64_t)t * R * D, lda, nullptr, WtS, D + H, g, G, 0.f, xbias, 0);
       has_x = 1;
     }
     const int32_t* tok = r.ptable ? r.gather + (int64_t)t * R : nullptr;
@@ -371,6 +376,15 @@ void Engine::lstm_forward_step(LstmRun& r, int t) {
   }
   if (hp) gemm_tn((int)R, G, H, hp, H, nullptr, WtS + D, D + H, g, G, 1.f, nullptr, 0);
   lstm_pointwise_fwd(cx, g, bias, cp, r.mask ? r.mask + (int64_t)t * R : nullptr, r.c + slot * R * H, r.h + slot * R * H, R, H);
+}
+
+// the per-step x-projection of a `step_xproj` run, issued by the caller on the stream of its choice (cx.stream)
+void Engine::lstm_forward_xproj(LstmRun& r, int t) {
+  const int H = r.H, D = r.D, G = 4 * r.H;
+  const int64_t R = r.R;
+  VD_REQUIRE(r.tc && r.step_xproj && r.saved && r.x, VD_E_STATE, "lstm_forward_xproj: not a per-step projected run");
+  gemm_tn((int)R, G, D, r.x + (int64_t)t * R * D, D, nullptr, Wtp(r.wseg), D + H, r.gates + (int64_t)t * R * G, G, 0.f,
+          Wp(r.wseg + 1), 0);
 }
 
 void Engine::lstm_forward(LstmRun& r, bool save) {
@@ -397,8 +411,15 @@ static int64_t wavefront_min_rows() {
   return v;
 }
 
-void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb) {
+static bool three_streams_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VD_THREE_STREAMS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) {
   const bool pipelined = math_mode == VD_MATH_TF32 && l2.H % 64 == 0 && sb != nullptr && sb != sa && l2.R >= wavefront_min_rows();
+  const bool three = pipelined && sc != nullptr && sc != sa && sc != sb && three_streams_enabled();
   cx.stream = sa;
   if (!pipelined) {
     lstm_forward(l1, true);
@@ -414,12 +435,25 @@ void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaSt
   VD_CUDA_CHECK(cudaStreamWaitEvent(sb, e0, 0));
   cx.stream = sb;
   lstm_forward_begin(l2, true);
+  l2.xproj_external = three;
   for (int t = 0; t < l1.T; ++t) {
     cx.stream = sa;
     lstm_forward_step(l1, t);
     cudaEvent_t e = pool_event(1 + t);
     VD_CUDA_CHECK(cudaEventRecord(e, sa));
-    VD_CUDA_CHECK(cudaStreamWaitEvent(sb, e, 0));
+    if (three) {
+      // layer 2's x-projection of step t needs h1_t only: on its own stream it runs beside layer 2's step t-1, so
+      // each of the three chains advances by ONE kernel per time step
+      VD_CUDA_CHECK(cudaStreamWaitEvent(sc, e, 0));
+      if (t == 0) VD_CUDA_CHECK(cudaStreamWaitEvent(sc, e0, 0));
+      cx.stream = sc;
+      lstm_forward_xproj(l2, t);
+      cudaEvent_t ex = pool_event(1 + l1.T + t);
+      VD_CUDA_CHECK(cudaEventRecord(ex, sc));
+      VD_CUDA_CHECK(cudaStreamWaitEvent(sb, ex, 0));
+    } else {
+      VD_CUDA_CHECK(cudaStreamWaitEvent(sb, e, 0));
+    }
     cx.stream = sb;
     lstm_forward_step(l2, t);
   }
@@ -523,11 +557,12 @@ void Engine::lstm_backward(LstmRun& r, const float* dh_all, const float* dh_last
 // BPTT wavefront of two stacked layers: layer-1 step t needs d(h1_t) = da2_t Wx2^T, produced per step on layer 2's
 // stream, so the two recurrences again run one step apart.
 void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2, const float* dc_last2, const float* dh_last1,
-                                const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb) {
+                                const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) {
   const int H = l2.H, G = 4 * l2.H;
   const int64_t R = l2.R;
   float* dx2 = arena.get<float>((int64_t)l2.T * R * l2.D);      // = gradient wrt layer-1 outputs, all steps
   const bool pipelined = math_mode == VD_MATH_TF32 && H % 128 == 0 && sb != nullptr && sb != sa && R >= wavefront_min_rows();
+  const bool three = pipelined && sc != nullptr && sc != sa && sc != sb && three_streams_enabled();
   cx.stream = sa;
   if (!pipelined) {
     lstm_backward(l2, nullptr, dh_last2, dc_last2, dx2, nullptr, nullptr);
@@ -545,10 +580,17 @@ void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2,
   for (int t = l2.T - 1; t >= 0; --t) {
     cx.stream = sb;
     lstm_backward_step(l2, t);
-    gemm_tn((int)R, l2.D, G, l2.da + (int64_t)t * R * G, G, nullptr, Wx2, G, dx2 + (int64_t)t * R * l2.D, l2.D, 0.f, nullptr, 0);
     cudaEvent_t e = pool_event(1 + t);
-    VD_CUDA_CHECK(cudaEventRecord(e, sb));
-    VD_CUDA_CHECK(cudaStreamWaitEvent(sa, e, 0));
+    if (three) {
+      // d(h1_t) = da2_t Wx2 needs layer 2's step t only: on its own stream it runs beside layer 2's step t-1
+      VD_CUDA_CHECK(cudaEventRecord(e, sb));
+      VD_CUDA_CHECK(cudaStreamWaitEvent(sc, e, 0));
+      cx.stream = sc;
+    }
+    gemm_tn((int)R, l2.D, G, l2.da + (int64_t)t * R * G, G, nullptr, Wx2, G, dx2 + (int64_t)t * R * l2.D, l2.D, 0.f, nullptr, 0);
+    cudaEvent_t ex = three ? pool_event(1 + l2.T + t) : e;
+    VD_CUDA_CHECK(cudaEventRecord(ex, cx.stream));
+    VD_CUDA_CHECK(cudaStreamWaitEvent(sa, ex, 0));
     cx.stream = sa;
     lstm_backward_step(l1, t);
   }
@@ -605,10 +647,10 @@ void Engine::encoder_forward(const vd_batch* b) {
     hist2 = make_run(db.Th, N, H, H, seg("hist.lstm2.weight"), nullptr, nullptr, ids_h);
   }
   // The 2nd layer consumes every step of the 1st, so encoder LSTMs always keep all steps (T*N*H is small).
-  auto run_two = [&](LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb) { lstm_pair_forward(l1, l2, sa, sb); };
+  auto run_two = [&](LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) { lstm_pair_forward(l1, l2, sa, sb, sc); };
   // The history and question LSTM chains are independent until the fusion/attention stage: the history chain runs
   // on the side stream (its tiny per-step kernels are latency-bound; overlapping the two chains hides half of it).
-  if (cfg.useHist) { fork_side(); run_two(hist1, hist2, side_stream, side2_stream); back_to_main(); }
+  if (cfg.useHist) { fork_side(); run_two(hist1, hist2, side_stream, side2_stream, side3_stream); back_to_main(); }
   // question branch
   xq = arena.get<float>(N * db.Tq * E);
   embed_rows(cx, xq, Wp(0), ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
@@ -626,7 +668,7 @@ void Engine::encoder_forward(const vd_batch* b) {
     ques1 = make_run(db.Tq, N, E, H, seg("ques.lstm1.weight"), xq, nullptr, ids_q);
   }
   ques2 = make_run(db.Tq, N, H, H, seg("ques.lstm2.weight"), nullptr, nullptr, ids_q);
-  run_two(ques1, ques2, main_stream, main2_stream);
+  run_two(ques1, ques2, main_stream, main2_stream, main3_stream);
   join_side();
   const float* q3 = ques2.h_last();
   const float* h3 = cfg.useHist ? hist2.h_last() : nullptr;
@@ -797,14 +839,14 @@ void Engine::encoder_backward(const float* dEnc) {
   if (cfg.useHist) {
     fork_side();
     float* dx1 = arena.get<float>(N * db.Th * E);
-    lstm_pair_backward(hist1, hist2, dh3, nullptr, nullptr, nullptr, dx1, side_stream, side2_stream);
+    lstm_pair_backward(hist1, hist2, dh3, nullptr, nullptr, nullptr, dx1, side_stream, side2_stream, side3_stream);
     embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
     back_to_main();
   }
   {
     int D1 = ques1.D;
     float* dx1 = arena.get<float>(N * db.Tq * D1);
-    lstm_pair_backward(ques1, ques2, dq3, conn_dc_l2, conn_dh_l1, conn_dc_l1, dx1, main_stream, main2_stream);
+    lstm_pair_backward(ques1, ques2, dq3, conn_dc_l2, conn_dh_l1, conn_dc_l1, dx1, main_stream, main2_stream, main3_stream);
     embed_scatter_add(cx, dWp(0), dx1, D1, ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
     if (cfg.enc == ENC_HREA) {
       float* die = arena.get<float>(N * cfg.IE);

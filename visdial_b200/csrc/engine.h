@@ -59,6 +59,7 @@ struct LstmRun {
   // forward run state (lstm_forward_begin / _step)
   bool tc = false;                   // fused tcgen05 step kernels
   bool step_xproj = false;           // dense input projected per step (layer-2 of a pipelined pair) instead of batched
+  bool xproj_external = false;       // ... and that per-step projection is issued by the caller (on its own stream)
   const float* ptable = nullptr;     // (V+1, 4H) projection table for embedding-gathered inputs
   // backward run state (lstm_backward_begin / _step / _end)
   float* da = nullptr; float* dc_carry = nullptr; float* dh_rec = nullptr;
@@ -160,10 +161,13 @@ struct Engine {
   void lstm_backward_step(LstmRun& r, int t);
   void lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float* dc0_out);
   // two stacked SeqLSTMs as a wavefront: layer 2 step t runs (on its own stream) as soon as layer 1 step t is done
-  void lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb);
+  // (sc: a third stream for the inter-layer contraction of every step — layer 2's x-projection forward, layer 1's
+  //  incoming gradient backward — which depends on one layer's step t only, not on the other layer's recurrence)
+  void lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc);
   void lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2, const float* dc_last2, const float* dh_last1,
-                          const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb);
-  cudaStream_t main2_stream = nullptr, side2_stream = nullptr;
+                          const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc);
+  void lstm_forward_xproj(LstmRun& r, int t);
+  cudaStream_t main2_stream = nullptr, side2_stream = nullptr, main3_stream = nullptr, side3_stream = nullptr;
   // The disc decoder's option LSTM (disc.lua:4-20) does not depend on the encoder until the final dot product, and its
   // BPTT does not feed the encoder's: both run on their own low-priority stream, concurrently with the encoder's
   // latency-bound chains (which keep priority for SMs as they free up).

@@ -173,18 +173,19 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
 // row" (the TMEM side) and "4 lanes = one row's 64 bytes" (the global side, coalesced 64-byte runs instead of one
 // 16-byte piece of 32 different lines per instruction, which is what saturated L1TEX before).
 constexpr int STG_ARR_BYTES = 32 * 16 * 4;
-template <int BN, int MODE, int CG> struct StageCfg {
+template <int BN, int MODE, int CG, int EW = EPI_WARPS> struct StageCfg {
   static constexpr bool ON = MODE == MODE_GENERIC || (CG == 2 && (BN == 256 || (BN == 128 && MODE == MODE_LSTM_BWD)));
   static constexpr int ARR = !ON ? 0 : (MODE == MODE_GENERIC ? 1 : MODE == MODE_LSTM_FWD ? 6 : 7);
-  static constexpr int BYTES = EPI_WARPS * ARR * STG_ARR_BYTES;
+  static constexpr int BYTES = EW * ARR * STG_ARR_BYTES;
 };
-template <int BN, int CG = 1, int STG_BYTES = 0> struct SmemLayout {
+template <int BN, int CG = 1, int STG_BYTES = 0, int MAXST = 16> struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;        // 16 KB (this CTA's 128 rows)
   static constexpr int B_BYTES = (BN / CG) * BK * 4; // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int WANT = (B_BYTES == 32768) ? 4 : (B_BYTES == 16384) ? 6 : (B_BYTES == 8192) ? 8 : 10;   // small tiles are latency-bound: deeper
   static constexpr int FIT = (232448 - 1024 - 256 - STG_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = WANT < FIT ? WANT : FIT;
+  static constexpr int STAGES0 = WANT < FIT ? WANT : FIT;
+  static constexpr int STAGES = STAGES0 < MAXST ? STAGES0 : MAXST;   // MAXST = 4: the half-size CTAs that share an SM
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 };
@@ -246,12 +247,16 @@ __device__ __forceinline__ void stg_put8(float* stg, int arr, int row, int sub, 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MODE, int CG>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// EW = epilogue warps.  8 (320 threads, one CTA per SM) for the SM-filling kernels; 4 (192 threads, 4 pipeline stages,
+// TWO CTAs per SM) for the few-row encoder kernels: those are latency-bound, so a CTA that owns a whole SM mostly
+// waits — and, run beside the option stream, what they cost is SM time, not FLOPs.
+template <int BN, int MODE, int CG, int EW = EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ EpiMaps em, const Params p) {
-  using SC = StageCfg<BN, MODE, CG>;
-  using L = SmemLayout<BN, CG, SC::BYTES>;
+  using SC = StageCfg<BN, MODE, CG, EW>;
+  using L = SmemLayout<BN, CG, SC::BYTES, (EW == 4 ? 4 : 16)>;
+  constexpr int NH = EW / 4;                         // epilogue warps per TMEM lane quarter = column slices per tile
   constexpr int STAGES = L::STAGES;
   constexpr int TM = BM * CG;                        // rows per tile: 128, or 256 for a CTA pair
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
@@ -275,7 +280,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS * CG); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EW * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (CG == 2) cluster_sync_all();                  // peer barriers exist before anyone signals them
@@ -386,7 +391,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int n0 = nt * BN;
         float* stg = stg_all + (warp - 2) * (SC::ARR * 32 * 16);
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+        for (int c = half * (BN / NH); c < (half + 1) * (BN / NH); c += 16) {
           if (n0 + c >= p.N) break;                 // warp-uniform
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
@@ -435,7 +440,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // staged epilogue: 16 hidden units at a time through the warp's swizzled staging tile
           float* stg = stg_all + (warp - 2) * (SC::ARR * 32 * 16);
 #pragma unroll 1
-          for (int c = half * (HB / 2); c < (half + 1) * (HB / 2); c += 16) {
+          for (int c = half * (HB / NH); c < (half + 1) * (HB / NH); c += 16) {
             const int j = j0 + c;
             if (lane == 0) bulk_wait_read0();    // the previous group's TMA stores have finished reading the staging tile
             __syncwarp();
@@ -494,7 +499,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         } else {
 #pragma unroll 1
-        for (int c = half * (HB / 2); c < (half + 1) * (HB / 2); c += 8) {
+        for (int c = half * (HB / NH); c < (half + 1) * (HB / NH); c += 8) {
           const int j = j0 + c;
           float a[4][8], x[4][8], cp[8];
           // issue the global loads first so that they overlap the TMEM read
@@ -550,7 +555,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if constexpr (SC::ON) {
           float* stg = stg_all + (warp - 2) * (SC::ARR * 32 * 16);
 #pragma unroll 1
-          for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+          for (int c = half * (BN / NH); c < (half + 1) * (BN / NH); c += 16) {
             const int j = j0 + c;
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
@@ -607,7 +612,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         } else {
 #pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
+        for (int c = half * (BN / NH); c < (half + 1) * (BN / NH); c += 8) {
           const int j = j0 + c;
           float dh[8], g[4][8], cp[8], cc[8], dc[8], ex[8];
           if (row_ok && !masked) {
@@ -833,15 +838,19 @@ static CUtensorMap make_tmap(const float* base, int64_t rows, int64_t cols, int6
 
 static bool tma_ok(const float* p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
 
-template <int BN, int MODE, int CG = 1>
+template <int BN, int MODE, int CG = 1, int EW = EPI_WARPS>
 static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, const Params& p, int num_tiles,
                    const EpiMaps* epi = nullptr) {
-  using L = SmemLayout<BN, CG, StageCfg<BN, MODE, CG>::BYTES>;
+  using L = SmemLayout<BN, CG, StageCfg<BN, MODE, CG, EW>::BYTES, (EW == 4 ? 4 : 16)>;
+  constexpr int THREADS = 64 + 32 * EW;
   static EpiMaps none = {};
   const EpiMaps& em = epi ? *epi : none;
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    if (EW == 4)      // two of these CTAs per SM: ask for the full shared-memory carve-out
+      VD_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN, MODE, CG, EW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   // Persistent grid, balanced waves: with pmax CTAs (pairs) available the tiles need ceil(tiles/pmax) rounds; the
@@ -854,21 +863,27 @@ static void launch(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB, 
   };
   if (CG == 1) {
     int grid = balanced(cx.sms());
-    k_tc_gemm<BN, MODE, 1><<<grid, NTHREADS, L::TOTAL, cx.stream>>>(tA, tB, em, p);
+    k_tc_gemm<BN, MODE, 1, EW><<<grid, THREADS, L::TOTAL, cx.stream>>>(tA, tB, em, p);
   } else {
     // CTA pairs: a 2-CTA cluster per 256-row tile, one pair per TPC (num_tiles counts 256-row tiles here)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * balanced(cx.sms() / 2));
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = cx.stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    VD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, MODE, 2>, tA, tB, em, p));
+    VD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tc_gemm<BN, MODE, 2, EW>, tA, tB, em, p));
   }
   check_launch(cx, "k_tc_gemm");
+}
+
+static bool small_ew4() {          // VD_SMALL_EW4=0: the few-row kernels as one 320-thread CTA per SM (A/B)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VD_SMALL_EW4"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 static int small_narrow() {
@@ -905,7 +920,8 @@ bool gemm_tn_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda,
     launch<128, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 128), &em);
   } else {
     CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 64);
-    launch<64, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 64), &em);
+    if (small_ew4()) launch<64, MODE_GENERIC, 1, 4>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 64), &em);
+    else launch<64, MODE_GENERIC>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 64), &em);
   }
   return true;
 }
@@ -968,7 +984,8 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
     launch<256, MODE_LSTM_FWD>(cx, tA, tB, p, tiles_big);
   } else {                                   // few rows (encoder LSTMs): 16 hidden units per tile, 4x the CTAs
     CUtensorMap tB = make_tmap(WtS_h, 4 * (int64_t)H, H, ldw, 16);
-    launch<64, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 16));
+    if (small_ew4()) launch<64, MODE_LSTM_FWD, 1, 4>(cx, tA, tB, p, cdiv(R, BM) * (H / 16));
+    else launch<64, MODE_LSTM_FWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 16));
   }
   return true;
 }
@@ -1013,7 +1030,8 @@ bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, con
     launch<128, MODE_LSTM_BWD>(cx, tA, tB, p, tiles_big);
   } else {
     CUtensorMap tB = make_tmap(Wh, H, 4 * (int64_t)H, 4 * (int64_t)H, 32);
-    launch<32, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
+    if (small_ew4()) launch<32, MODE_LSTM_BWD, 1, 4>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
+    else launch<32, MODE_LSTM_BWD>(cx, tA, tB, p, cdiv(R, BM) * (H / 32));
   }
   return true;
 }
