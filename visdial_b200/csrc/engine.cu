@@ -902,7 +902,11 @@ void Engine::options_forward_async() {
   }
   cudaStream_t prev = cx.stream;
   cx.stream = s;
-  if (opt_overlap) cx.sm_budget = cx.sm_count - opt_reserve_sms;   // leave SMs to the encoder's concurrent chains
+  if (opt_overlap) {                                                // leave SMs to the encoder's concurrent chains
+    static int fwd_reserve = -1;                                    // VD_OPT_RESERVE_FWD: A/B knob, default = the common reserve
+    if (fwd_reserve < 0) { const char* e = getenv("VD_OPT_RESERVE_FWD"); fwd_reserve = e ? (atoi(e) & ~1) : 1 << 20; }
+    cx.sm_budget = cx.sm_count - (fwd_reserve == 1 << 20 ? opt_reserve_sms : std::min(fwd_reserve, cx.sm_count - 16));
+  }
   ids_o = arena.get<int32_t>(Ro * db.To);
   transpose_ids(cx, db.options, ids_o, Ro, db.To);
   opt = make_run(db.To, Ro, cfg.E, cfg.H, seg("opt.lstm.weight"), nullptr, ids_o, nullptr);   // disc.lua:4-5: no maskzero
