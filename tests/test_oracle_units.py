@@ -210,3 +210,54 @@ def test_gen_retrieval_matches_lhood_definition():
     ranks = O.retrieve_batch(O.Ctx(), p, P, b, use_gt=False)
     assert ranks.shape == (10, p["numOptions"])
     assert sorted(ranks[0].tolist()) == list(range(1, p["numOptions"] + 1))
+
+
+def test_seq_lstm_against_an_independent_lstm_implementation():
+    """torch.nn.LSTM (ATen's CPU kernels, the lineage of Torch7's nn) as a second opinion on the [upstream] SeqLSTM
+    semantics the oracle restates: same recurrence, gate blocks permuted ([i f o g] here, [i f g o] there), weights
+    stored input-major here and output-major there, one bias here and two there.  Outputs AND all gradients agree."""
+    torch.manual_seed(0)
+    T, N, D, H = 5, 3, 4, 6
+    W = torch.randn(D + H, 4 * H, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(4 * H, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(T, N, D, dtype=torch.float64, requires_grad=True)
+    h0 = torch.randn(N, H, dtype=torch.float64)
+    c0 = torch.randn(N, H, dtype=torch.float64)
+    h, c = O.seq_lstm(x, W, b, h0, c0)
+    (h.sin().sum() + c[-1].cos().sum()).backward()
+
+    ref = torch.nn.LSTM(D, H, num_layers=1).double()
+    perm = torch.cat([torch.arange(0, 2 * H), torch.arange(3 * H, 4 * H), torch.arange(2 * H, 3 * H)])   # ours -> [i f g o]
+    with torch.no_grad():
+        ref.weight_ih_l0.copy_(W.detach()[:D][:, perm].t())
+        ref.weight_hh_l0.copy_(W.detach()[D:][:, perm].t())
+        ref.bias_ih_l0.copy_(b.detach()[perm])
+        ref.bias_hh_l0.zero_()
+    x2 = x.detach().clone().requires_grad_(True)
+    out, (hn, cn) = ref(x2, (h0[None], c0[None]))
+    (out.sin().sum() + cn[0].cos().sum()).backward()
+    assert torch.allclose(h, out, atol=1e-12) and torch.allclose(c[-1], cn[0], atol=1e-12)
+    assert torch.allclose(x.grad, x2.grad, atol=1e-11)
+    gW = torch.cat([ref.weight_ih_l0.grad.t(), ref.weight_hh_l0.grad.t()], 0)        # [i f g o] columns, input-major
+    inv = torch.argsort(perm)
+    assert torch.allclose(W.grad, gW[:, inv], atol=1e-11)
+    assert torch.allclose(b.grad, ref.bias_ih_l0.grad[inv], atol=1e-11)
+
+
+def test_criterions_against_torch_functional():
+    """nn.CrossEntropyCriterion (mean over rows) and MaskZero(ClassNLL, sizeAverage=false) on LogSoftMax rows
+    [upstream] against torch.nn.functional."""
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    scores = torch.randn(7, 10, dtype=torch.float64)
+    gt = torch.randint(1, 11, (7,))
+    loss = O.cross_entropy_mean(scores, gt) if hasattr(O, "cross_entropy_mean") else None
+    want = F.cross_entropy(scores, gt - 1)
+    if loss is not None:
+        assert abs(float(loss) - float(want)) < 1e-12
+    p = small_params("mn-att-ques-im-hist", "disc")
+    P = torch_params(p, E.init_parameters(p, seed=3))
+    b = torch_batch(small_batch(p, B=2))
+    out = O.forward_backward(O.Ctx(), p, P, b, only_forward=True)
+    want = F.cross_entropy(out["decOut"], b["answer_ind"].reshape(-1) - 1)                  # decoders/disc.lua + model.lua:330
+    assert abs(out["loss"] - float(want)) < 1e-5 * max(1.0, abs(float(want)))
