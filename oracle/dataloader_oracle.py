@@ -11,7 +11,7 @@ Every function cites the reference lines it follows.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 

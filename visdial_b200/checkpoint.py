@@ -18,16 +18,12 @@ here, and load in the reference as a table of the right shape.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Dict, Optional
 
 import numpy as np
 
 from . import t7
-from ._lib import check
 from .engine import layout as _layout
-
-_PARAM_KEYS_SKIP = ("gpuid",)
 
 
 def _plain(v):

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(256) k_gather_img(const float4* __restrict__ s
 // ------------------------------------------------------------------------------------------------
 struct Corpus {
   Engine* eng = nullptr;
+  int gpuid = 0;
   int n = 0, R = 0, Lq = 0, La = 0, Lc = 0, K = 0, m = 0, Wh = 0, nimg = 0;
   int useHist = 0, concat = 0, useIm = 0, maxHistoryLen = 0, start_tok = 0, end_tok = 0;
   int64_t img_elems = 0;
@@ -239,6 +240,7 @@ struct Corpus {
     return d;
   }
   ~Corpus() {
+    cudaSetDevice(gpuid);
     for (void* p : owned) cudaFree(p);
     for (int s = 0; s < 2; ++s) {
       OutSet& o = out[s];
@@ -268,6 +270,7 @@ Corpus* corpus_create(Engine* eng, const vd_corpus_desc* d) {
   VD_REQUIRE(d->numOptions == eng->cfg.K, VD_E_SHAPE, "opt:size(3) != params.numOptions");
   std::unique_ptr<Corpus> c(new Corpus());
   c->eng = eng;
+  c->gpuid = eng->cfg.gpuid;
   c->n = d->numThreads; c->R = d->numRounds; c->Lq = d->maxQuesLen; c->La = d->maxAnsLen; c->Lc = d->maxCapLen;
   c->K = d->numOptions; c->m = d->numOptList; c->nimg = d->numImages;
   c->useHist = d->useHistory != 0; c->concat = d->concatHistory != 0; c->useIm = d->useIm != 0;
@@ -392,6 +395,7 @@ void corpus_get_batch(Corpus* c, const int64_t* inds, int n, int decoder_gen, vd
   VD_REQUIRE(n > 0, VD_E_SHAPE, "batch must hold at least one dialog");
   VD_REQUIRE(decoder_gen >= 0 && decoder_gen <= 2, VD_E_BADARG, "decoder_gen must be 0, 1 or 2");
   Engine* eng = c->eng;
+  VD_CUDA_CHECK(cudaSetDevice(c->gpuid));
   cudaStream_t st = eng->main_stream;
   LaunchCtx& cx = eng->cx;
   const int R = c->R, K = c->K, La = c->La, Lq = c->Lq;
@@ -493,6 +497,7 @@ void corpus_read(Corpus* c, const char* name, void* host_dst, int64_t* elems) {
   VD_REQUIRE(p != nullptr, VD_E_STATE, "this corpus does not hold that tensor (useHistory / useIm off)");
   *elems = cnt;
   if (host_dst) {
+    VD_CUDA_CHECK(cudaSetDevice(c->gpuid));
     VD_CUDA_CHECK(cudaStreamSynchronize(c->eng->main_stream));
     VD_CUDA_CHECK(cudaMemcpy(host_dst, p, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
   }
