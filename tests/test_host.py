@@ -133,6 +133,23 @@ def test_gloo_world2_plumbing():
     assert t == 2.0                          # timing is the max over ranks
 
 
+def test_eval_split_partition_walks_every_dialog_once_in_order():
+    """Dataloader(rank, world): contiguous per-rank ranges of an evaluation split, walked in batches; the rank-ordered
+    concatenation is 0..n-1 (what dist.gather_ranks relies on), for ragged sizes too."""
+    from visdial_b200.dataloader import eval_partition, test_batch_indices
+    for n, world, bs in ((2064, 8, 32), (17, 4, 5), (3, 4, 2), (40, 1, 16)):
+        seen = []
+        for rank in range(world):
+            lo, hi = eval_partition(n, rank, world)
+            start = 0
+            while start < hi - lo:
+                inds, nxt = test_batch_indices(start, bs, lo, hi)
+                assert 0 < len(inds) <= bs and nxt > start
+                seen += inds.tolist()
+                start = nxt
+        assert seen == list(range(n)), (n, world, bs)
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` needs no GPU: one JSON line with the contract's keys (a bounded CPU sample)."""
     import json

@@ -159,13 +159,36 @@ class Corpus:
             pass
 
 
+def eval_partition(n: int, rank: int, world: int):
+    """Contiguous share [lo, hi) of an n-dialog evaluation split for `rank` (never splits a dialog)."""
+    from .dist import shard_range
+    return shard_range(n, rank, world)
+
+
+def test_batch_indices(startId: int, batchSize: int, lo: int, hi: int):
+    """getTestBatch's index range (dataloader.lua:347-357) inside a rank's partition [lo, hi): `startId` counts from the
+    partition's first dialog (0-based); returns (global 0-based dialog indices, nextStartId)."""
+    nxt = min(hi - lo, startId + batchSize)
+    return lo + np.arange(startId, nxt), nxt
+
+
+test_batch_indices.__test__ = False          # not a pytest test
+
+
 class Dataloader:
     """`dataloader` table of the reference (dataloader.lua:5-8) bound to one engine."""
 
-    def __init__(self, eng: Engine, seed: int = 1234):
+    def __init__(self, eng: Engine, seed: int = 1234, rank: int = 0, world: int = 1):
+        """`rank` / `world`: data-parallel use (one process per GPU, SURVEY §8e).  Every rank holds the whole corpus;
+        training batches are drawn independently per rank (seed + rank: the global batch is world x batchSize dialogs
+        sampled with replacement, as the reference samples one batch, :326); evaluation splits are partitioned into
+        `world` contiguous dialog ranges, so that a rank-ordered gather of the per-rank results
+        (visdial_b200.dist.gather_ranks) is the unsharded order.  No collective touches the data path."""
         self.eng = eng
-        self.rng = np.random.default_rng(seed)
+        self.rank, self.world = int(rank), int(world)
+        self.rng = np.random.default_rng(seed + 7919 * self.rank)
         self.numThreads: Dict[str, int] = {}
+        self.part: Dict[str, tuple] = {}             # dtype -> (first dialog, one past the last) of this rank
         self.corpus: Dict[str, Corpus] = {}
 
     def initialize(self, opt: dict, subsets, data: Dict[str, Dict[str, np.ndarray]], vocab_size_no_specials: int = None):
@@ -185,7 +208,8 @@ class Dataloader:
         for dtype in subsets:
             c = Corpus(self.eng, data[dtype], opt, self.word2ind["<START>"], self.word2ind["<END>"])
             self.corpus[dtype] = c
-            self.numThreads[dtype] = c.numThreads                                   # :94-105
+            self.part[dtype] = eval_partition(c.numThreads, self.rank, self.world) if dtype != "train" else (0, c.numThreads)
+            self.numThreads[dtype] = self.part[dtype][1] - self.part[dtype][0]      # :94-105 (this rank's share)
             self.maxQuesCount = c.R                                                 # :122
             self.numOptions = c.K                                                   # :112
             self.maxQuesLen = int(c.desc.maxQuesLen)                                # :124
@@ -231,8 +255,7 @@ class Dataloader:
 
     def getTestBatch(self, startId: int, params: dict, dtype: str = "val"):
         """`startId` is 0-based here (Lua's startId - 1); returns (batch, nextStartId) like :344-375."""
-        nxt = min(self.numThreads[dtype], startId + int(params["batchSize"]))       # :347-353
-        inds = np.arange(startId, nxt)                                              # :356-357
+        inds, nxt = test_batch_indices(startId, int(params["batchSize"]), *self.part[dtype])   # :347-357
         mode = 0 if params["decoder"] == "disc" else 2                              # :362-371
         return self.corpus[dtype].get_batch(inds, mode, with_num_rounds=True), nxt
 
