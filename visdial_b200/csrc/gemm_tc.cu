@@ -19,7 +19,7 @@ constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
 constexpr int EPI_WARPS = 8;     // 2 warps per TMEM lane quarter, each takes half of the tile's columns
-constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+// threads per CTA = 64 (TMA producer warp + MMA issuer warp) + 32 * epilogue warps (template parameter EW)
 
 enum { MODE_GENERIC = 0, MODE_LSTM_FWD = 1, MODE_LSTM_BWD = 2 };
 
