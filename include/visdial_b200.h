@@ -142,6 +142,16 @@ int vd_compute_ranks(vd_engine* e, const float* scores_dev, int32_t n_rows,
 /* utils.computeLhood (utils.lua:86-102) fused with the gen decoder: log-likelihood (N,100) of
  * every candidate answer, never materialising the (T,N,V) log-probs. */
 int vd_gen_option_lhood(vd_engine* e, const vd_batch* b, const float** lhood_dev);
+/* Model:generateAnswers (model.lua:432-613): the pieces its beam search / sampling loop drives on the device.
+ *  vd_encoder_rnn_state: enc.rnnLayers[level].output[Tq] / .cell[Tq] of the last vd_encoder_forward, (N,H) device
+ *    pointers, level = 0 | 1 (model.lua:480-483); both NULL for encoders without .rnnLayers (mn-att, :491-501).
+ *  vd_gen_decoder_step: decoder:forward(tokens) for ONE time step on `rows` independent rows with
+ *    .userPrevOutput / .userPrevCell = h_prev[l] / c_prev[l] (l = 0, 1; (rows,H) device pointers, NULL = zeros)
+ *    (model.lua:517-526, gen.lua:3-27).  tokens: HOST int32 (rows).  Returns device pointers, valid until the next
+ *    vd_encoder_forward: log-probabilities (rows,V) (all-zero row for a pad token, MaskZero) and the new state. */
+int vd_encoder_rnn_state(vd_engine* e, int32_t level, const float** h_last_dev, const float** c_last_dev);
+int vd_gen_decoder_step(vd_engine* e, int32_t rows, const int32_t* tokens_host, const float* const* h_prev,
+                        const float* const* c_prev, const float** logp_dev, const float** h_out, const float** c_out);
 
 /* ---- optimiser step (model.lua:96-105 + optim_updates.lua:62-91) ---------------------------- */
 /* all-reduce(SUM)/world of dW when a communicator is attached, then clamp(-5,5), then adam.

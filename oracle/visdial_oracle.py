@@ -522,6 +522,101 @@ def retrieve_batch(ctx: Ctx, cfg, P, batch, use_gt: bool = True) -> Tensor:
         return compute_ranks(scores, gt)                              # :427
 
 
+def decoder_gen_step(cfg, P, tokens: Tensor, H, C):
+    """One time step of decoders/gen.lua:3-27 with explicit state, as Model:generateAnswers drives it through
+    `.userPrevOutput / .userPrevCell` (model.lua:517-524): tokens (N) -> (log-probs (N,V), [h1,h2], [c1,c2])."""
+    x = lookup_table_mask_zero(P["wordEmbed.weight"], tokens.view(1, -1))
+    o1, c1 = seq_lstm(x, *lstm_p(P, "dec.lstm1"), h0=H[0], c0=C[0], maskzero=True, manual_bptt=False)
+    o2, c2 = seq_lstm(o1, *lstm_p(P, "dec.lstm2"), h0=H[1], c0=C[1], maskzero=True, manual_bptt=False)
+    flat = o2[0]
+    keep = (flat.abs().sum(1) != 0).to(flat.dtype).unsqueeze(1)
+    logits = linear(flat, P["dec.out.weight"], P["dec.out.bias"]) * keep
+    return torch.log_softmax(logits, 1) * keep, [o1[0], o2[0]], [c1[0], c2[0]]
+
+
+def _initial_beam_state(state, encOut: Tensor, it: int, beam: int):
+    """model.lua:478-503: decoder state of round `it` replicated over the beams."""
+    Hd = encOut.shape[1]
+    rl = state.get("rnnLayers")
+    if rl is not None:                                                # encoders that expose .rnnLayers
+        H = [rl[l][0][-1][it] for l in range(len(rl))]                # :482 output[Tq][iter]
+        Cc = [rl[l][1][-1][it] for l in range(len(rl))]               # :483 cell[Tq][iter]
+        H[len(rl) - 1] = encOut[it]                                   # :484-486
+    else:                                                             # :491-501
+        H = [encOut.new_zeros(Hd), encOut[it]]
+        Cc = [encOut.new_zeros(Hd), encOut.new_zeros(Hd)]
+    return [h.repeat(beam, 1) for h in H], [c.repeat(beam, 1) for c in Cc]
+
+
+def generate_answers(ctx: Ctx, cfg, P, batch, start_token: int, end_token: int, beam_size: int = 5, beam_len: int = 20,
+                     sample_words: bool = False, temperature: float = 1.0, generator: Optional[torch.Generator] = None,
+                     strict: bool = True):
+    """Model:generateAnswers for ONE dialog (model.lua:432-613; the reference loops convId = 1..numThreads with a batch
+    of one dialog, :462-465).  Beam search (:472-579) restated literally, quirks included: step 2 expands one beam only
+    (:510), finished hypotheses leave the pool with their un-normalised score (:546-547), columns beyond the number of
+    surviving candidates keep their previous content (:559), the answer is the best FINISHED beam (:575-579; the
+    reference indexes nil — raises here — when none finished).  Sampling (:581-602): multinomial over
+    exp(logp / T) with the decoder fed its own samples (`decoderConnect`, gen.lua:63-68).
+    Returns a list of 10 dicts {answer: LongTensor (beam_len) zero-padded, score, length} (beam) or
+    {answer: LongTensor (beam_len + 1)} (sampling)."""
+    assert cfg["decoder"] == "gen", "Sampling/beam search only for generative model"        # :434-437
+    with torch.no_grad():
+        inputs = prepare_inputs(cfg, batch)
+        encOut, state = ENCODERS[cfg["encoder"]](Ctx(train=False), cfg, P, inputs)           # :468 (evaluate mode)
+        R = encOut.shape[0]
+        out = []
+        if not sample_words:
+            for it in range(R):                                                              # :474
+                beams = torch.zeros(beam_len, beam_size, dtype=torch.long)                   # :479
+                H, Cc = _initial_beam_state(state, encOut, it, beam_size)
+                beams[0] = start_token                                                       # :506
+                scores = torch.zeros(beam_size, dtype=torch.float64)                         # :507
+                finished = []                                                                # :508
+                for step in range(1, beam_len):                                              # :510 (Lua step = step + 1)
+                    cands = []
+                    explore = 1 if step == 1 else beam_size                                  # :516
+                    logp, nH, nC = decoder_gen_step(cfg, P, beams[step - 1], H, Cc)          # :519-526
+                    for w in range(explore):                                                 # :529
+                        top_p, top_i = torch.topk(logp[w], beam_size, largest=True, sorted=True)   # :538-542
+                        for cnd in range(beam_size):                                         # :544
+                            cb = beams[:, w].clone()
+                            tok = int(top_i[cnd]) + 1                                        # class index -> 1-based token id
+                            cb[step] = tok
+                            sc = float(scores[w]) + float(top_p[cnd])
+                            if tok == end_token:                                             # :548-549
+                                finished.append({"answer": cb, "length": step + 1, "score": sc})
+                            else:                                                            # :550-553
+                                cands.append((sc, cb, [h[w].clone() for h in nH], [c[w].clone() for c in nC]))
+                    cands.sort(key=lambda t: -t[0])                                          # :558 (ties: stable here)
+                    for k in range(min(len(cands), beam_size)):                              # :560-569
+                        beams[:, k] = cands[k][1]
+                        for lv in range(2):
+                            H[lv][k] = cands[k][2][lv]
+                            Cc[lv][k] = cands[k][3][lv]
+                        scores[k] = cands[k][0]
+                finished.sort(key=lambda d: -d["score"])                                     # :572
+                if not finished:
+                    if strict:
+                        raise IndexError("no beam reached <END> within beamLen (model.lua:575 indexes nil here)")
+                    out.append(None)
+                    continue
+                out.append(finished[0])                                                      # :575
+        else:
+            H0, C0 = gen_forward_connect(state, encOut)                                      # forwardBackward(batch, true, true)
+            H = [h if h is not None else encOut.new_zeros(R, encOut.shape[1]) for h in H0]
+            Cc = [c if c is not None else encOut.new_zeros(R, encOut.shape[1]) for c in C0]
+            tok = torch.full((R,), start_token, dtype=torch.long)                            # :582
+            seq = [tok.clone()]
+            for _ in range(beam_len):                                                        # :584
+                logp, H, Cc = decoder_gen_step(cfg, P, tok, H, Cc)                           # :586-588
+                probs = torch.exp(logp / temperature)                                        # :590
+                tok = torch.multinomial(probs, 1, generator=generator).squeeze(1) + 1
+                seq.append(tok.clone())
+            ans = torch.stack(seq, 1)                                                        # :594
+            out = [{"answer": ans[i]} for i in range(R)]
+    return out
+
+
 def clamp_adam(W: Tensor, dW: Tensor, state: dict, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
     """model.lua:96-99 + model_utils/optim_updates.lua:62-91 on the flat vectors (in place)."""
     dW.clamp_(-5.0, 5.0)

@@ -216,6 +216,45 @@ def test_model_retrieve_over_the_device_dataloader(enc, dec):
     d2.close(); model.engine.close()
 
 
+@pytest.mark.parametrize("enc", ["lf-ques", "hrea-ques-im-hist", "mn-att-ques-im-hist"])
+def test_generate_answers_matches_oracle(enc):
+    """Model:generateAnswers (model.lua:432-613) — beam search and sampling driven through vd_gen_decoder_step on
+    batches the device dataloader assembles — against oracle.generate_answers on the same dialog (fp32 math mode)."""
+    import torch
+    from helpers import torch_batch, torch_params
+    from oracle import visdial_oracle as O
+    from visdial_b200 import init_parameters
+    params = small_params(enc, "gen", vocabSize=9)
+    concat = "lf" in enc and "hist" in enc
+    raw = make_corpus(params, 12, 40, seed=77, max_ques_len=8, max_ans_len=6, max_cap_len=14,
+                      ques_len_cap=5 if concat else None, ans_len_cap=4 if concat else None)
+    V = params["vocabSize"]
+    orc = D.DataloaderOracle(raw, use_history="hist" in enc, concat_history=concat, use_im="im" in enc, start=V - 1, end=V,
+                             img_norm=True, att="att" in enc)
+    model = Model(dict(params, batchSize=1), seed=3)
+    model.engine.set_math_mode(1)
+    flat = init_parameters(params, seed=3)
+    model.engine.set_parameters(flat)
+    dl = Dataloader(model.engine).initialize(_opt(params, True), ["val"], {"val": raw})
+    P = torch_params(params, flat)
+    for conv in (0, 3, 7):
+        got = model.generateAnswers(dl, "val", {"beamSize": 3, "beamLen": 6, "maxThreads": conv + 1}, strict=False)[conv]["dialog"]
+        tb = torch_batch(orc.get_index_data(np.array([conv])))
+        with torch.no_grad():
+            want = O.generate_answers(O.Ctx(), params, P, tb, V - 1, V, beam_size=3, beam_len=6, strict=False)
+        assert len(got) == len(want) == 10
+        for g, w in zip(got, want):
+            assert (g is None) == (w is None)
+            if g is not None:
+                assert g["answer"] == w["answer"].tolist() and g["length"] == w["length"]
+                assert abs(g["score"] - w["score"]) < 1e-4
+    samp = model.generateAnswers(dl, "val", {"sampleWords": 1, "temperature": 0.8, "beamLen": 5, "maxThreads": 2, "seed": 4})
+    assert len(samp) == 2 and all(len(d["dialog"]) == 10 for d in samp)
+    assert all(len(r["answer"]) == 6 and r["answer"][0] == V - 1 and all(1 <= t <= V for t in r["answer"])
+               for d in samp for r in d["dialog"])
+    dl.close(); model.engine.close()
+
+
 def test_initialize_from_files(tmp_path):
     """dataloader:initialize's file half (dataloader.lua:13-129): visdial_params.json + visdial_data.h5 + data_img.h5
     named as prepro.py / prepro_img_*.lua name them -> the same batches as the in-memory path."""

@@ -212,6 +212,104 @@ def test_gen_retrieval_matches_lhood_definition():
     assert sorted(ranks[0].tolist()) == list(range(1, p["numOptions"] + 1))
 
 
+def _gen_setup(enc, seed=3, V=9):
+    p = small_params(enc, "gen", vocabSize=V)
+    P = torch_params(p, E.init_parameters(p, seed=seed))
+    b = torch_batch(small_batch(p, B=1, seed=5))
+    return p, P, b
+
+
+def _teacher_forced_score(p, P, b, it, seq):
+    """sum of log-probs of seq[1:] given seq[:-1] for round `it`, through the SEQUENCE decoder (decoder_gen)"""
+    inputs = O.prepare_inputs(p, b)
+    encOut, state = O.ENCODERS[p["encoder"]](O.Ctx(train=False), p, P, inputs)
+    H0, C0 = O.gen_forward_connect(state, encOut)
+    N = encOut.shape[0]
+    a_in = torch.zeros(len(seq) - 1, N, dtype=torch.long)
+    a_in[:, it] = torch.tensor(seq[:-1])
+    logp = O.decoder_gen(O.Ctx(train=False), p, P, a_in, H0, C0)
+    return sum(float(logp[t, it, seq[t + 1] - 1]) for t in range(len(seq) - 1))
+
+
+def _textbook_beam(p, P, b, it, S, Eend, B, L):
+    """Plain beam search scored by TEACHER FORCING through the sequence decoder (decoder_gen) — an independent code path
+    from the step decoder generate_answers drives.  Returns (best finished sequence, score, quirk_free): `quirk_free` is
+    False when some step left fewer than B live hypotheses, the case in which the reference keeps a stale beam column
+    (model.lua:559) and the two algorithms legitimately differ."""
+    V = p["vocabSize"]
+    live, done, ok = [(0.0, [S])], [], True
+    for step in range(1, L):
+        cands = []
+        for sc, seq in (live[:1] if step == 1 else live):
+            nxt = sorted(((_teacher_forced_score(p, P, b, it, seq + [a]) , a) for a in range(1, V + 1)), reverse=True)[:B]
+            for s2, a in nxt:
+                (done if a == Eend else cands).append((s2, seq + [a]))
+        cands.sort(key=lambda t: -t[0])
+        ok = ok and len(cands) >= B
+        live = cands[:B]
+    done.sort(key=lambda t: -t[0])
+    return (done[0][1], done[0][0], ok) if done else (None, None, ok)
+
+
+@pytest.mark.parametrize("enc,min_checked", [("lf-ques", 3), ("hrea-ques-im-hist", 1), ("mn-att-ques-im-hist", 0)])
+def test_beam_search_matches_a_textbook_beam_search(enc, min_checked):
+    """Model:generateAnswers (model.lua:472-579): same winner and score as a plain beam search whenever the reference's
+    stale-column quirk is not triggered (with random weights <END> is rare: `min_checked` = rounds known to finish)."""
+    V, B, L = 9, 3, 6
+    p, P, b = _gen_setup(enc, V=V)
+    S, Eend = V - 1, V
+    checked = 0
+    with torch.no_grad():
+        got = O.generate_answers(O.Ctx(), p, P, b, S, Eend, beam_size=B, beam_len=L, strict=False)
+        for it in range(10):
+            best, want, ok = _textbook_beam(p, P, b, it, S, Eend, B, L)
+            if not ok:
+                continue
+            if best is None:
+                assert got[it] is None
+                continue
+            assert got[it]["answer"][:len(best)].tolist() == best and got[it]["length"] == len(best)
+            assert abs(got[it]["score"] - want) < 1e-5
+            checked += 1
+    assert checked >= min_checked
+
+
+def test_beam_of_one_is_greedy_and_unfinished_beams_raise():
+    p, P, b = _gen_setup("lf-ques")
+    V = p["vocabSize"]
+    with torch.no_grad():
+        inputs = O.prepare_inputs(p, b)
+        encOut, state = O.ENCODERS[p["encoder"]](O.Ctx(train=False), p, P, inputs)
+        # greedy roll-out of round 2 with the step decoder
+        H, C = O._initial_beam_state(state, encOut, 2, 1)
+        tok, seq = torch.tensor([V - 1]), [V - 1]
+        for _ in range(30):
+            logp, H, C = O.decoder_gen_step(p, P, tok, H, C)
+            tok = logp.argmax(1) + 1
+            seq.append(int(tok))
+            if int(tok) == V:
+                break
+        if seq[-1] == V and len(seq) <= 12:
+            got = O.generate_answers(O.Ctx(), p, P, b, V - 1, V, beam_size=1, beam_len=12)
+            assert got[2]["answer"][:len(seq)].tolist() == seq
+        with pytest.raises(IndexError):                      # one step, beam 1: <END> is not the arg-max -> nothing finished
+            first = O.decoder_gen_step(p, P, torch.tensor([V - 1]), *O._initial_beam_state(state, encOut, 0, 1))[0]
+            assert int(first.argmax(1)) + 1 != V
+            O.generate_answers(O.Ctx(), p, P, b, V - 1, V, beam_size=1, beam_len=2)
+
+
+def test_sampling_feeds_the_decoder_its_own_tokens():
+    p, P, b = _gen_setup("hrea-ques-im-hist")
+    V = p["vocabSize"]
+    g = torch.Generator().manual_seed(7)
+    a = O.generate_answers(O.Ctx(), p, P, b, V - 1, V, beam_len=6, sample_words=True, temperature=0.7, generator=g)
+    g = torch.Generator().manual_seed(7)
+    c = O.generate_answers(O.Ctx(), p, P, b, V - 1, V, beam_len=6, sample_words=True, temperature=0.7, generator=g)
+    assert len(a) == 10 and all(x["answer"].shape == (7,) and int(x["answer"][0]) == V - 1 for x in a)
+    assert all(torch.equal(x["answer"], y["answer"]) for x, y in zip(a, c))
+    assert all(1 <= int(t) <= V for x in a for t in x["answer"])
+
+
 def test_seq_lstm_against_an_independent_lstm_implementation():
     """torch.nn.LSTM (ATen's CPU kernels, the lineage of Torch7's nn) as a second opinion on the [upstream] SeqLSTM
     semantics the oracle restates: same recurrence, gate blocks permuted ([i f o g] here, [i f g o] there), weights

@@ -87,6 +87,9 @@ SIGNATURES = {
     "vd_retrieve": [_H, _P(vd_batch), C.c_int32, C.c_void_p],
     "vd_compute_ranks": [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
     "vd_gen_option_lhood": [_H, _P(vd_batch), _P(C.c_void_p)],
+    "vd_encoder_rnn_state": [_H, C.c_int32, _P(C.c_void_p), _P(C.c_void_p)],
+    "vd_gen_decoder_step": [_H, C.c_int32, C.c_void_p, _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
+                            _P(C.c_void_p)],
     "vd_clamp_adam_step": [_H, C.c_float],
     "vd_comm_unique_id": [C.c_void_p],
     "vd_comm_init": [_H, C.c_void_p, C.c_int32, C.c_int32],

@@ -208,6 +208,28 @@ int vd_gen_option_lhood(vd_engine* h, const vd_batch* b, const float** lhood_dev
   VD_TRY({ (void)b; Engine* e = ENG(h); e->gen_option_lhood(); if (lhood_dev) *lhood_dev = e->lhood; })
 }
 
+int vd_encoder_rnn_state(vd_engine* h, int32_t level, const float** h_last, const float** c_last) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(e->have_fwd, VD_E_STATE, "vd_encoder_rnn_state before vd_encoder_forward");
+    VD_REQUIRE(level == 0 || level == 1, VD_E_BADARG, "level must be 0 or 1");
+    const bool has_layers = e->cfg.enc != vd::ENC_MN_ATT;            // the encoders that expose .rnnLayers (gen.lua:31)
+    const vd::LstmRun& r = level == 0 ? e->ques1 : e->ques2;
+    if (h_last) *h_last = has_layers ? r.h_last() : nullptr;
+    if (c_last) *c_last = has_layers ? r.c_last() : nullptr;
+  })
+}
+int vd_gen_decoder_step(vd_engine* h, int32_t rows, const int32_t* tokens_host, const float* const* h_prev,
+                        const float* const* c_prev, const float** logp_dev, const float** h_out, const float** c_out) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    e->gen_decoder_step(rows, tokens_host, h_prev, c_prev);
+    if (logp_dev) *logp_dev = e->gstep_logp;
+    if (h_out) { h_out[0] = e->gstep1.h; h_out[1] = e->gstep2.h; }
+    if (c_out) { c_out[0] = e->gstep1.c; c_out[1] = e->gstep2.c; }
+  })
+}
+
 int vd_clamp_adam_step(vd_engine* h, float lr) { VD_TRY({ ENG(h)->clamp_adam_step(lr); }) }
 
 int vd_comm_unique_id(void* id_out) { VD_TRY({ NOTNULL(id_out); vd::comm_unique_id(id_out); }) }

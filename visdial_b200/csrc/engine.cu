@@ -1107,6 +1107,32 @@ void Engine::gen_option_lhood() {
   }
 }
 
+// Model:generateAnswers' inner decoder call (model.lua:517-526): decoders/gen.lua:3-27 for ONE time step on `rows`
+// independent rows with explicit previous state.  Same kernels, in the same order, as decoder_forward's gen branch with
+// Ta = 1 (dense embedded input, maskzero on the token, MaskZero'd Linear + LogSoftMax).
+void Engine::gen_decoder_step(int64_t rows, const int32_t* tokens_host, const float* const* h_prev, const float* const* c_prev) {
+  VD_REQUIRE(cfg.dec == DEC_GEN, VD_E_STATE, "gen_decoder_step needs the gen decoder");
+  VD_REQUIRE(have_fwd, VD_E_STATE, "gen_decoder_step before encoder_forward");
+  VD_REQUIRE(rows > 0 && tokens_host != nullptr, VD_E_BADARG, "rows / tokens");
+  VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  cx.stream = main_stream;
+  const int E = cfg.E, H = cfg.H, V = cfg.V;
+  int32_t* tok = arena.get<int32_t>(rows);
+  VD_CUDA_CHECK(cudaMemcpyAsync(tok, tokens_host, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
+  VD_CUDA_CHECK(cudaStreamSynchronize(cx.stream));               // tokens_host may be a temporary of the caller
+  float* xa = arena.get<float>(rows * E);
+  embed_rows(cx, xa, Wp(0), tok, rows, E, dropcfg(0.f), 0);
+  gstep1 = make_run(1, rows, E, H, seg("dec.lstm1.weight"), xa, nullptr, tok);
+  gstep1.h0 = h_prev ? h_prev[0] : nullptr; gstep1.c0 = c_prev ? c_prev[0] : nullptr;
+  lstm_forward(gstep1, true);
+  gstep2 = make_run(1, rows, H, H, seg("dec.lstm2.weight"), gstep1.h, nullptr, tok);
+  gstep2.h0 = h_prev ? h_prev[1] : nullptr; gstep2.c0 = c_prev ? c_prev[1] : nullptr;
+  lstm_forward(gstep2, true);
+  gstep_logp = arena.get<float>(rows * V);
+  linear_fwd(seg("dec.out.weight"), gstep2.h, rows, gstep_logp, 0);
+  logsoftmax_rows(cx, gstep_logp, tok, rows, V);                // gen.lua:23-24 (MaskZero)
+}
+
 // model.lua:96-99 + optim_updates.lua:62-91
 void Engine::clamp_adam_step(float lr) {
   VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));

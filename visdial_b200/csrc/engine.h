@@ -193,6 +193,10 @@ struct Engine {
   const float* backward_connect();
   void retrieve(const vd_batch* b, int use_gt, int32_t* ranks_host);
   void gen_option_lhood();
+  // Model:generateAnswers: one gen-decoder step with explicit state (model.lua:517-526)
+  LstmRun gstep1, gstep2;
+  float* gstep_logp = nullptr;
+  void gen_decoder_step(int64_t rows, const int32_t* tokens_host, const float* const* h_prev, const float* const* c_prev);
   void clamp_adam_step(float lr);
   void allreduce_grads();
 };

@@ -253,6 +253,12 @@ class Dataloader:
         inds = self.rng.integers(0, self.numThreads["train"], size=size)            # :326 (uniform with replacement)
         return self.corpus["train"].get_batch(inds, 0 if params["decoder"] == "disc" else 1)   # :329-337
 
+    def getIndexData(self, inds0, params: dict, dtype: str) -> DeviceBatch:
+        """dataloader.getIndexData (dataloader.lua:378-433) for explicit dialog indices (0-based, within this rank's
+        share of the split): the call Model:generateAnswers makes per dialog (model.lua:464)."""
+        inds = self.part[dtype][0] + np.asarray(inds0, dtype=np.int64).reshape(-1)
+        return self.corpus[dtype].get_batch(inds, 1)
+
     def getTestBatch(self, startId: int, params: dict, dtype: str = "val"):
         """`startId` is 0-based here (Lua's startId - 1); returns (batch, nextStartId) like :344-375."""
         inds, nxt = test_batch_indices(startId, int(params["batchSize"]), *self.part[dtype])   # :347-357

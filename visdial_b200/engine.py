@@ -310,6 +310,43 @@ class Engine:
         check(self.lib.vd_retrieve(self.h, C.byref(batch.c), int(use_gt), out.ctypes.data))
         return out
 
+    # ---- Model:generateAnswers building blocks (model.lua:432-613) ---------------------------------------------
+    def encoder_rnn_state(self, level: int, rows: int):
+        """enc.rnnLayers[level+1].output[Tq] / .cell[Tq] as (rows,H) device tensors, or (None, None)."""
+        hp, cp = C.c_void_p(), C.c_void_p()
+        check(self.lib.vd_encoder_rnn_state(self.h, int(level), C.byref(hp), C.byref(cp)))
+        H = self.params["rnnHiddenSize"]
+        if not hp.value:
+            return None, None
+        return DeviceTensor(self, hp.value, (rows, H)), DeviceTensor(self, cp.value, (rows, H))
+
+    def gen_decoder_step(self, tokens: np.ndarray, h_prev, c_prev):
+        """One decoder step on len(tokens) rows.  h_prev / c_prev: two device pointers (int) or None each.
+        Returns (log-probs (rows,V) numpy, [h1, h2] numpy, [c1, c2] numpy)."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        rows = tokens.shape[0]
+        arr = C.c_void_p * 2
+        hp = arr(*[C.c_void_p(p) if p else C.c_void_p(None) for p in (h_prev or (None, None))])
+        cp = arr(*[C.c_void_p(p) if p else C.c_void_p(None) for p in (c_prev or (None, None))])
+        logp, ho, co = C.c_void_p(), arr(), arr()
+        check(self.lib.vd_gen_decoder_step(self.h, rows, tokens.ctypes.data, hp, cp, C.byref(logp), ho, co))
+        H, V = self.params["rnnHiddenSize"], self.params["vocabSize"]
+        return (DeviceTensor(self, logp.value, (rows, V)).numpy(),
+                [DeviceTensor(self, ho[i], (rows, H)).numpy() for i in range(2)],
+                [DeviceTensor(self, co[i], (rows, H)).numpy() for i in range(2)])
+
+    def upload(self, dev_ptr: int, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        check(self.lib.vd_memcpy_h2d(self.h, C.c_void_p(dev_ptr), a.ctypes.data, a.nbytes))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.vd_device_alloc(self.h, C.byref(p), int(nbytes)))
+        return p.value
+
+    def device_free(self, dev_ptr: int):
+        check(self.lib.vd_device_free(self.h, C.c_void_p(dev_ptr)))
+
     def clamp_adam_step(self, lr: float):
         check(self.lib.vd_clamp_adam_step(self.h, float(lr)))
 

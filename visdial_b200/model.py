@@ -128,6 +128,120 @@ class Model:
         self.wrapper.training()
         return np.concatenate(ranks, 0)
 
+    # ---- beam search / sampling (model.lua:432-613, generate.lua) ---------------------------------------------
+    def generateAnswers(self, dataloader, dtype="val", params=None, strict=True):
+        """Model:generateAnswers: per dialog, encoder forward on the device, then the decoder driven one step at a time
+        through vd_gen_decoder_step; the hypothesis bookkeeping runs on the host exactly as the Lua does (it indexes
+        GPU tensors scalar by scalar).  Returns the reference's answerTable with token-id lists (and text when the
+        dataloader carries ind2word).  `strict=False` yields None for a round where no beam reached <END> (the
+        reference indexes nil there, model.lua:575)."""
+        if self.params["decoder"] == "disc":                                            # :434-437
+            raise ValueError("Sampling/beam search only for generative model")
+        params = params or {}
+        sampleWords = bool(params.get("sampleWords", 0) == 1)                           # :443
+        temperature = float(params.get("temperature", 1.0))
+        beamSize, beamLen = int(params.get("beamSize", 5)), int(params.get("beamLen", 20))
+        startToken, endToken = dataloader.word2ind["<START>"], dataloader.word2ind["<END>"]   # :453-454
+        numThreads = int(params.get("maxThreads") or dataloader.numThreads[dtype])      # :455
+        ind2word = getattr(dataloader, "ind2word", None)
+        rng = np.random.default_rng(int(params.get("seed", 1234)))
+        eng, H = self.engine, self.params["rnnHiddenSize"]
+        words = (lambda ids: " ".join(ind2word.get(int(t), "<UNK>") for t in ids if int(t) > 0)) if ind2word else None
+        state_buf = [eng.device_alloc(max(beamSize, self.params["maxQuesCount"]) * H * 4) for _ in range(4)]
+        answerTable = []
+        try:
+            for convId in range(numThreads):
+                self.wrapper.evaluate()                                                 # :460
+                batch = dataloader.getIndexData(np.array([convId]), self.params, dtype)  # :462-463
+                encOut = self.forwardBackward(batch, True, True).numpy()                # :467 (N,H), N = 10
+                ques = batch["ques_fwd"].reshape(-1, batch.c.Tq)
+                N = encOut.shape[0]
+                layers = [eng.encoder_rnn_state(l, N) for l in range(2)]
+                has_layers = layers[0][0] is not None
+                encH = [(layers[l][0].numpy(), layers[l][1].numpy()) for l in range(2)] if has_layers else None
+                threadAnswers = []
+
+                def step(tokens, Hs, Cs):
+                    n = len(tokens)
+                    for i, a in enumerate(Hs + Cs):
+                        eng.upload(state_buf[i], a[:n])
+                    return eng.gen_decoder_step(tokens, state_buf[0:2], state_buf[2:4])
+
+                if not sampleWords:
+                    for it in range(N):                                                 # :472
+                        beams = np.zeros((beamLen, beamSize), dtype=np.int64)           # :479
+                        if has_layers:                                                  # :482-491
+                            Hs = [encH[0][0][it], encOut[it]]
+                            Cs = [encH[0][1][it], encH[1][1][it]]
+                        else:                                                           # :493-501
+                            Hs = [np.zeros(H, np.float32), encOut[it]]
+                            Cs = [np.zeros(H, np.float32), np.zeros(H, np.float32)]
+                        Hs = [np.repeat(h[None], beamSize, 0).astype(np.float32) for h in Hs]
+                        Cs = [np.repeat(c[None], beamSize, 0).astype(np.float32) for c in Cs]
+                        beams[0] = startToken                                           # :506
+                        scores = np.zeros(beamSize, dtype=np.float64)                   # :507
+                        finishBeams = []
+                        for stp in range(1, beamLen):                                   # :510
+                            cands = []
+                            exploreSize = 1 if stp == 1 else beamSize                   # :516
+                            decOut, nH, nC = step(beams[stp - 1], Hs, Cs)               # :519-526
+                            for wordId in range(exploreSize):                           # :529
+                                order = np.argsort(-decOut[wordId], kind="stable")[:beamSize]   # :538-542 topk, sorted
+                                for candId in range(beamSize):                          # :544
+                                    candBeam = beams[:, wordId].copy()
+                                    tok = int(order[candId]) + 1
+                                    candBeam[stp] = tok
+                                    sc = float(scores[wordId]) + float(decOut[wordId, order[candId]])
+                                    if tok == endToken:                                 # :548
+                                        finishBeams.append({"beam": candBeam, "length": stp + 1, "score": sc})
+                                    else:
+                                        cands.append((sc, candBeam, [h[wordId].copy() for h in nH], [c[wordId].copy() for c in nC]))
+                            cands.sort(key=lambda t: -t[0])                             # :558
+                            for candId in range(min(len(cands), beamSize)):             # :560-569
+                                beams[:, candId] = cands[candId][1]
+                                for lv in range(2):
+                                    Hs[lv][candId] = cands[candId][2][lv]
+                                    Cs[lv][candId] = cands[candId][3][lv]
+                                scores[candId] = cands[candId][0]
+                        finishBeams.sort(key=lambda d: -d["score"])                     # :572
+                        if not finishBeams:
+                            if strict:
+                                raise IndexError("no beam reached <END> within beamLen (model.lua:575 indexes nil here)")
+                            threadAnswers.append(None)
+                            continue
+                        best = finishBeams[0]
+                        entry = {"question": ques[it].tolist(), "answer": best["beam"].tolist(), "score": best["score"],
+                                 "length": best["length"]}
+                        if words:
+                            entry["question_text"], entry["answer_text"] = words(ques[it]), words(best["beam"])
+                        threadAnswers.append(entry)
+                else:                                                                   # :581-602
+                    if has_layers:                                                      # forwardConnect, gen.lua:30-42
+                        Hs, Cs = [encH[0][0], encOut], [encH[0][1], encH[1][1]]
+                    else:
+                        Hs, Cs = [np.zeros((N, H), np.float32), encOut], [np.zeros((N, H), np.float32)] * 2
+                    tok = np.full(N, startToken, dtype=np.int64)
+                    seq = [tok.copy()]
+                    for _ in range(beamLen):
+                        decOut, Hs, Cs = step(tok, Hs, Cs)                              # :586-588 (+ decoderConnect)
+                        p = np.exp(decOut.astype(np.float64) / temperature)             # :590
+                        p /= p.sum(1, keepdims=True)
+                        tok = np.array([rng.choice(p.shape[1], p=p[i]) + 1 for i in range(N)], dtype=np.int64)
+                        seq.append(tok.copy())
+                    ans = np.stack(seq, 1)
+                    for it in range(N):
+                        entry = {"question": ques[it].tolist(), "answer": ans[it].tolist()}
+                        if words:
+                            entry["question_text"], entry["answer_text"] = words(ques[it]), words(ans[it])
+                        threadAnswers.append(entry)
+                self.wrapper.training()                                                 # :605
+                img = getattr(dataloader, "unique_img_" + dtype, None)
+                answerTable.append({"image_id": img[convId] if img else convId, "dialog": threadAnswers})   # :606
+        finally:
+            for p in state_buf:
+                eng.device_free(p)
+        return answerTable
+
     # ---- checkpoints (train.lua:33-34,78-80,99-102,120-121; evaluate.lua:58-91) -------------------------------
     def save(self, path: str, final: bool = False):
         """torch.save(path, {modelW, optims, modelParams}) — `final` = the model_final.t7 form (float weights, no optims)."""
