@@ -202,9 +202,8 @@ def run_ours(args, rank, local, world):
     p["batchSize"] = args.batch
     model = Model(p, seed=1234)                       # same seed on every rank -> identical replicas
     eng = model.engine
-    if args.math == "fp32":
-        from visdial_b200 import VD_MATH_FP32
-        eng.set_math_mode(VD_MATH_FP32)
+    from visdial_b200 import VD_MATH_F16, VD_MATH_FP32, VD_MATH_TF32
+    eng.set_math_mode({"fp32": VD_MATH_FP32, "tf32": VD_MATH_TF32, "f16": VD_MATH_F16}[args.math])
     vdist.attach_engine(eng, rank, world)
 
     # a few distinct batches per rank, in pinned host memory (weak scaling: B dialogs per GPU)
@@ -376,7 +375,7 @@ def run_ours(args, rank, local, world):
     step_flops = 3.0 * FWD_FLOP_PER_ROUND * args.batch * 10
     line = {"metric": METRIC, "value": value, "unit": "QA-rounds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"f16": "f16 operands (option LSTM) + tf32 operands (everything else), fp32 accumulate", "tf32": "tf32", "fp32": "f32"}[args.math], "data": "synthetic",
             "config": {"workload": "C4 mn-att-ques-im-hist+disc train step (pool5 14x14x512, 10 rounds, 100 options x 20 tokens, V=10000)",
                        "dialogs_per_gpu": args.batch, "global_batch_dialogs": args.batch * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (LSTM gates/activations, >10 GB) >> 126 MB L2; 4 rotating input batches"},
@@ -416,7 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="dialogs per GPU (BASELINE config 4: 32)")
-    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--math", default="f16", choices=["f16", "tf32", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=8)

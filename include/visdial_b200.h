@@ -113,6 +113,8 @@ int vd_set_training(vd_engine* e, int32_t training);   /* wrapper:training()/:ev
 int vd_set_dropout_seed(vd_engine* e, uint64_t seed, uint64_t iteration);
 #define VD_MATH_TF32 0        /* dense contractions on tcgen05 tensor cores, TF32 operands, fp32 accumulate */
 #define VD_MATH_FP32 1        /* same contractions on CUDA cores in fp32 (verification mode) */
+#define VD_MATH_F16 2         /* TF32 mode + the many-row option LSTM (disc.lua:4-20) with fp16 operands and fp16 saved state
+                                 (h, gates, da, x-projection table), fp32 accumulation, fp32 cell state and gradients */
 int vd_set_math_mode(vd_engine* e, int32_t mode);
 /* Scheduling knob (results are identical either way).  on = 1 (default): the disc decoder's option LSTM (disc.lua:4-20),
  * which does not depend on the encoder until the final dot product, runs on its own stream concurrently with the
@@ -192,6 +194,10 @@ int vd_gemm_tn(vd_engine* e, int32_t M, int32_t N, int32_t K, const float* A, in
                float* C, int64_t ldc, float beta, const float* bias, int32_t act);
 int vd_gemm_atb(vd_engine* e, int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
                 float* C, int64_t ldc);
+/* test hook of the VD_MATH_F16 weight-gradient primitive: A (K x M) and B (K x N) fp32 DEVICE buffers are rounded to
+ * fp16, then C[m,n] += inv_scale * sum_k A[k,m] B[k,n] on tcgen05 kind::f16 (both operands MN-major). */
+int vd_gemm_atb16(vd_engine* e, int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                  float* C, int64_t ldc, float inv_scale);
 /* cudaProfilerStart / cudaProfilerStop (ncu --profile-from-start off) */
 int vd_profiler_range(vd_engine* e, int32_t start);
 /* flush L2 by writing a scratch buffer larger than L2 (bench hygiene) */

@@ -12,7 +12,8 @@ from helpers import flat_from_named, small_params, torch_batch, torch_params
 from oracle import philox
 from oracle import visdial_oracle as O
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLD = sorted(g for g in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
+              if not os.path.basename(g).startswith("c4_b32"))      # the benched-size fixture has its own test file
 
 
 def _load(path):

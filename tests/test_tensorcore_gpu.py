@@ -15,7 +15,7 @@ import torch
 from helpers import full_params, seg_slices, small_params, torch_batch, torch_params
 from oracle import philox
 from oracle import visdial_oracle as O
-from visdial_b200 import VD_MATH_FP32, VD_MATH_TF32, Batch, Engine, init_parameters
+from visdial_b200 import VD_MATH_F16, VD_MATH_FP32, VD_MATH_TF32, Batch, Engine, init_parameters
 from visdial_b200._lib import check
 from visdial_b200.synthetic import make_batch
 
@@ -110,6 +110,23 @@ def test_gemm_atb_vs_fp64(eng, M, N, K):
         for d in (dA, dB, dC):
             d.free()
         assert np.abs(got - ref).max() < tol, mode
+
+
+@pytest.mark.parametrize("M,N,K,inv", [(128, 256, 64, 1.0), (512, 2048, 6400, 0.25), (512, 2048, 333, 1.0), (256, 1024, 70000, 2.0 ** -7)])
+def test_gemm_atb16_vs_fp64(eng, M, N, K, inv):
+    """VD_MATH_F16 weight-gradient primitive (both operands MN-major fp16, kind::f16, fp32 accumulate, split-K): exact
+    products of the fp16-rounded operands, so only the fp32 accumulation order separates it from fp64."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((K, M)).astype(np.float16).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float16).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = C0 + inv * (A.astype(np.float64).T @ B.astype(np.float64))
+    dA, dB, dC = Dev(eng, A), Dev(eng, B), Dev(eng, C0)
+    check(eng.lib.vd_gemm_atb16(eng.h, M, N, K, dA.p, M, dB.p, N, dC.p, N, inv))
+    got = dC.get()
+    for d in (dA, dB, dC):
+        d.free()
+    assert np.abs(got - ref).max() < 2e-6 * K * inv + 1e-5, float(np.abs(got - ref).max())
 
 
 def _rel(a, b):
@@ -275,3 +292,47 @@ def test_tf32_other_configs_at_reference_layer_sizes(enc, dec, B):
             continue
         assert _rel(g[s], r) < 3e-2, name
     eng.close()
+
+
+@pytest.mark.parametrize("B,T0", [(2, None), (11, None)])
+def test_f16_option_lstm_matches_oracle(B, T0):
+    """VD_MATH_F16: H = 256 and 100 options so that the option LSTM (B*10*100 >= 1024 rows) takes the fp16 CTA-pair kernels
+    (first step, recurrent steps, BPTT steps, MN-major weight gradient, fp16 segmented embedding gradient)."""
+    p = small_params("mn-att-ques-im-hist", "disc", rnnHiddenSize=256, embedSize=64, vocabSize=300, numOptions=100,
+                     commonEmbeddingSize=64, imgFeatureSize=64, imgSpatialSize=4, imgEmbedSize=32)
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, B, seed=7, max_ques_len=9, max_ans_len=6, max_cap_len=12, max_hist_len=14, empty_round_every=4)
+    P, tb = torch_params(p, flat), torch_batch(nb)
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3), structure="batched"), p, P, tb)
+    ev = O.forward_backward(O.Ctx(structure="batched"), p, P, tb, only_forward=True)
+    res = {}
+    for mode in (VD_MATH_TF32, VD_MATH_F16):
+        eng = Engine(p)
+        eng.set_math_mode(mode)
+        eng.set_parameters(flat)
+        eng.set_training(1)
+        eng.set_dropout_seed(11, 3)
+        eng.zero_grad()
+        loss = eng.forward_backward(Batch(nb))
+        g = eng.get_gradients()
+        eng.set_training(0)
+        b = Batch(nb)
+        eng.encoder_forward(b)
+        sc = eng.decoder_forward(b).numpy()
+        eng.close()
+        res[mode] = (loss, g, sc)
+    for mode in (VD_MATH_TF32, VD_MATH_F16):
+        loss, g, sc = res[mode]
+        assert abs(loss - ref["loss"]) < 5e-3 * max(1.0, abs(ref["loss"])), (mode, loss, ref["loss"])
+        dev = float(np.abs(sc - ev["decOut"].numpy()).max())
+        assert dev < 5e-3 * max(1.0, float(ev["decOut"].abs().max())), (mode, dev)
+        for name, s in seg_slices(p).items():
+            r = ref["grads"][name].numpy().ravel()
+            if np.abs(r).max() < 1e-7:
+                continue
+            assert _rel(g[s], r) < 3e-2, (mode, name, _rel(g[s], r))
+    # the fp16 option LSTM is in the TF32 error class: its deviation from the oracle stays within 2x the TF32 path's
+    for name in ("opt.lstm.weight", "opt.lstm.bias", "wordEmbed.weight"):
+        s = seg_slices(p)[name]
+        r = ref["grads"][name].numpy().ravel()
+        assert _rel(res[VD_MATH_F16][1][s], r) < 2.0 * _rel(res[VD_MATH_TF32][1][s], r) + 1e-3, name

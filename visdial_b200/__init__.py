@@ -6,4 +6,4 @@ class (model.lua:8-430) and the `utils` rank helpers, all calling libvisdial_b20
 C ABI of include/visdial_b200.h.  The same ABI is what lua/*.lua binds with LuaJIT FFI."""
 from .engine import Engine, Batch, DeviceTensor, init_parameters, split_parameters, layout, DEFAULT_PARAMS  # noqa: F401
 from .model import Model  # noqa: F401
-from ._lib import VdError, VD_MATH_FP32, VD_MATH_TF32  # noqa: F401
+from ._lib import VdError, VD_MATH_FP32, VD_MATH_TF32, VD_MATH_F16  # noqa: F401

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvisdial_b200.so")
 VD_OK = 0
 VD_MATH_TF32 = 0
 VD_MATH_FP32 = 1
+VD_MATH_F16 = 2
 VD_COMM_ID_BYTES = 128
 INIT_EMBED, INIT_LINEAR_W, INIT_LINEAR_B, INIT_LSTM_W, INIT_LSTM_B = range(5)
 
@@ -112,6 +113,8 @@ SIGNATURES = {
                    C.c_int64, C.c_float, C.c_void_p, C.c_int32],
     "vd_gemm_atb": [_H, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                     C.c_int64],
+    "vd_gemm_atb16": [_H, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                      C.c_int64, C.c_float],
     "vd_profiler_range": [_H, C.c_int32],
     "vd_flush_l2": [_H],
     "vd_corpus_create": [_H, _P(vd_corpus_desc), _P(C.c_void_p)],

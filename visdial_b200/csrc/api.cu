@@ -150,7 +150,7 @@ int vd_set_option_overlap(vd_engine* h, int32_t on, int32_t reserve_sms) {
   })
 }
 int vd_set_math_mode(vd_engine* h, int32_t mode) {
-  VD_TRY({ VD_REQUIRE(mode == VD_MATH_TF32 || mode == VD_MATH_FP32, VD_E_BADARG, "unknown math mode"); ENG(h)->math_mode = mode; })
+  VD_TRY({ VD_REQUIRE(mode == VD_MATH_TF32 || mode == VD_MATH_FP32 || mode == VD_MATH_F16, VD_E_BADARG, "unknown math mode"); ENG(h)->math_mode = mode; })
 }
 
 int vd_encoder_forward(vd_engine* h, const vd_batch* b, const float** encOut) {
@@ -327,6 +327,24 @@ int vd_gemm_atb(vd_engine* h, int32_t M, int32_t N, int64_t K, const float* A, i
     VD_REQUIRE(A && B && C, VD_E_BADARG, "null operand");
     VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
     e->gemm_atb(M, N, K, A, lda, nullptr, B, ldb, C, ldc);
+  })
+}
+int vd_gemm_atb16(vd_engine* h, int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                  float* C, int64_t ldc, float inv_scale) {
+  VD_TRY({
+    Engine* e = ENG(h);
+    VD_REQUIRE(A && B && C, VD_E_BADARG, "null operand");
+    VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
+    __half* A16 = nullptr; __half* B16 = nullptr; float* sc = nullptr;
+    VD_CUDA_CHECK(cudaMalloc((void**)&A16, (size_t)K * M * sizeof(__half)));
+    VD_CUDA_CHECK(cudaMalloc((void**)&B16, (size_t)K * N * sizeof(__half)));
+    VD_CUDA_CHECK(cudaMalloc((void**)&sc, sizeof(float)));
+    VD_CUDA_CHECK(cudaMemcpyAsync(sc, &inv_scale, sizeof(float), cudaMemcpyHostToDevice, e->cx.stream));
+    cvt_f32_to_f16(e->cx, A16, M, A, lda, K, M);
+    cvt_f32_to_f16(e->cx, B16, N, B, ldb, K, N);
+    gemm_atb16(e->cx, M, N, K, A16, M, B16, N, C, ldc, sc);
+    VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
+    cudaFree(A16); cudaFree(B16); cudaFree(sc);
   })
 }
 int vd_profiler_range(vd_engine* h, int32_t start) {

@@ -236,13 +236,13 @@ DropCfg Engine::dropcfg(float p) const {
 void Engine::gemm_tn(int M, int N, int K, const float* A, int64_t lda, const int32_t* gather, const float* B, int64_t ldb,
                      float* C, int64_t ldc, float beta, const float* bias, int act) {
   LaunchCtx::Scope sc(&cx, "gemm", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N));
-  if (math_mode == VD_MATH_TF32 && gemm_tn_tc(cx, M, N, K, A, lda, gather, B, ldb, C, ldc, beta, bias, act)) return;
+  if (tcmode() && gemm_tn_tc(cx, M, N, K, A, lda, gather, B, ldb, C, ldc, beta, bias, act)) return;
   gemm_tn_simt(cx, M, N, K, A, lda, gather, B, ldb, C, ldc, beta, bias, act);
 }
 void Engine::gemm_atb(int M, int N, int64_t K, const float* A, int64_t lda, const int32_t* gather, const float* B,
                       int64_t ldb, float* C, int64_t ldc) {
   LaunchCtx::Scope sc(&cx, "gemm_wgrad", 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N));
-  if (math_mode == VD_MATH_TF32 && gemm_atb_tc(cx, M, N, K, A, lda, gather, B, ldb, C, ldc)) return;
+  if (tcmode() && gemm_atb_tc(cx, M, N, K, A, lda, gather, B, ldb, C, ldc)) return;
   gemm_atb_simt(cx, M, N, K, A, lda, gather, B, ldb, C, ldc);
 }
 
@@ -311,8 +311,31 @@ void Engine::lstm_forward_begin(LstmRun& r, bool save) {
   // computed once per forward (E Wx^T: the 300-wide half of every step's contraction collapses into a
   // gather in the step epilogue); a dense input keeps the batched x-projection.  Each step is then ONE fused
   // kernel: recurrent tcgen05 GEMM + SeqLSTM pointwise epilogue.
-  r.tc = math_mode == VD_MATH_TF32 && H % 64 == 0;
+  r.tc = tcmode() && H % 64 == 0;
   r.ptable = nullptr;
+  // VD_MATH_F16: a many-row LSTM over embedding-gathered tokens (the option LSTM) keeps h, the activated gates, da and
+  // the projection table in fp16 and runs kind::f16 contractions (lstm16.cu); c, the accumulators and h_T stay fp32
+  r.f16 = math_mode == VD_MATH_F16 && r.gather && !r.x && !r.h0 && D == cfg.E && lstm16_shape_ok(R, H);
+  if (r.f16) {
+    float* pt = arena.get<float>((int64_t)(cfg.V + 1) * G);
+    gemm_tn(cfg.V + 1, G, D, Wp(0), cfg.E, nullptr, WtS, D + H, pt, G, 0.f, nullptr, 0);     // bias stays fp32, added per step
+    r.P16 = arena.get<__half>((int64_t)(cfg.V + 1) * G);
+    cvt_f32_to_f16(cx, r.P16, G, pt, G, cfg.V + 1, G);
+    r.Wh16 = arena.get<__half>((int64_t)G * H);
+    cvt_f32_to_f16(cx, r.Wh16, H, WtS + D, D + H, G, H);                                    // [4H, H]: B operand of the forward step
+    r.Whb16 = nullptr;
+    if (save) {
+      r.Whb16 = arena.get<__half>((int64_t)H * G);
+      cvt_f32_to_f16(cx, r.Whb16, G, Wp(r.wseg) + (int64_t)D * G, G, H, G);                 // [H, 4H]: B operand of the backward step
+    }
+    const int64_t slots = save ? r.T : 2;
+    r.h16 = arena.get<__half>(slots * R * H);
+    r.c = arena.get<float>(slots * R * H);
+    r.gates16 = save ? arena.get<__half>((int64_t)r.T * R * G) : nullptr;
+    r.h32_last = arena.get<float>(R * H);
+    r.h = nullptr; r.gates = nullptr;
+    return;
+  }
   // on the tensor-core path the bias is folded into the x-projection (table or GEMM epilogue), so the per-step
   // kernel reads one array less
   const float* xbias = r.tc ? bias : nullptr;
@@ -348,9 +371,28 @@ void Engine::lstm_forward_step(LstmRun& r, int t) {
   const float* hp = t > 0 ? r.h + pslot * R * H : r.h0;
   const float* cp = t > 0 ? r.c + pslot * R * H : r.c0;
   const bool per_step_x = !r.ptable && (!save || (r.tc && r.step_xproj));
+  if (r.f16) {
+    __half* g16 = save ? r.gates16 + (int64_t)t * R * G : nullptr;
+    const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
+    const int32_t* tok = r.gather + (int64_t)t * R;
+    float* h32 = t == r.T - 1 ? r.h32_last : nullptr;
+    if (t == 0) {       // no recurrent term: a streaming kernel, accounted outside the roofline class
+      LaunchCtx::Scope sc(&cx, "lstm_step_first", 0.0, R * (2.0 * G + 2.0 * G + 6.0 * H));
+      lstm16_first_step(cx, R, H, r.P16, tok, bias, cp, mk, g16, r.c + slot * R * H, r.h16 + slot * R * H, h32);
+    } else {
+      LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * H, R * (2.0 * G + 2.0 * G + 4.0 * H + 4.0 * H + 2.0 * H + 2.0 * H));
+      lstm16_step_fwd(cx, R, H, r.h16 + pslot * R * H, r.Wh16, r.P16, tok, bias, cp, mk, g16, r.c + slot * R * H,
+                      r.h16 + slot * R * H, h32);
+    }
+    return;
+  }
   // the big (option-LSTM) launches run alone on the GPU: they are the roofline kernel class; the 320-row encoder
   // steps overlap on 4 streams and are accounted separately
-  LaunchCtx::Scope sc(&cx, R >= 4096 ? "lstm_step" : "lstm_step_small", 2.0 * R * G * (H + ((r.ptable || per_step_x) ? D : 0)), 4.0 * R * (G + 4.0 * H));
+  // EXECUTED work only: a gathered x-projection is a table lookup, and a first step without initial state has no
+  // recurrent contraction at all (it is a streaming kernel, kept out of the roofline class)
+  const bool first_no_rec = r.tc && !hp;
+  LaunchCtx::Scope sc(&cx, first_no_rec ? "lstm_step_first" : (R >= 4096 ? "lstm_step" : "lstm_step_small"),
+                      first_no_rec ? 0.0 : 2.0 * R * G * (H + (per_step_x ? D : 0)), 4.0 * R * (G + 4.0 * H));
   if (r.tc) {
     const int32_t* mk = r.mask ? r.mask + (int64_t)t * R : nullptr;
     int has_x = 0;
@@ -418,7 +460,7 @@ static bool three_streams_enabled() {
 }
 
 void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) {
-  const bool pipelined = math_mode == VD_MATH_TF32 && l2.H % 64 == 0 && sb != nullptr && sb != sa && l2.R >= wavefront_min_rows();
+  const bool pipelined = tcmode() && l2.H % 64 == 0 && sb != nullptr && sb != sa && l2.R >= wavefront_min_rows();
   const bool three = pipelined && sc != nullptr && sc != sa && sc != sb && three_streams_enabled();
   cx.stream = sa;
   if (!pipelined) {
@@ -466,11 +508,20 @@ void Engine::lstm_backward_begin(LstmRun& r, const float* dh_all, const float* d
   VD_REQUIRE(r.saved, VD_E_STATE, "lstm_backward needs a forward run in training mode");
   const int H = r.H, G = 4 * r.H;
   const int64_t R = r.R, TR = (int64_t)r.T * R;
-  r.da = arena.get<float>(TR * G);
   r.dc_carry = arena.get<float>(R * H);
-  r.dh_rec = arena.get<float>(R * H);
+  if (!r.f16) {
+    r.da = arena.get<float>(TR * G);
+    r.dh_rec = arena.get<float>(R * H);
+  }
   r.bw_dh_all = dh_all; r.bw_dh_last = dh_last; r.bw_dc_last = dc_last;
-  r.bw_tc = math_mode == VD_MATH_TF32 && H % 128 == 0;
+  if (r.f16) {
+    VD_REQUIRE(dh_last && !dh_all && !dc_last, VD_E_STATE, "fp16 BPTT takes its gradient from the last step only");
+    r.da16 = arena.get<__half>(TR * G);
+    r.scale2 = arena.get<float>(4);
+    pick_grad_scale(cx, dh_last, R * H, reinterpret_cast<uint32_t*>(r.scale2 + 2), r.scale2);
+    return;
+  }
+  r.bw_tc = tcmode() && H % 128 == 0;
   if (r.bw_tc && dc_last)
     VD_CUDA_CHECK(cudaMemcpyAsync(r.dc_carry, dc_last, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
   else
@@ -486,7 +537,19 @@ void Engine::lstm_backward_step(LstmRun& r, int t) {
   float* da_t = r.da + (int64_t)t * R * G;
   const bool last = t == r.T - 1;
   const float* ext = r.bw_dh_all ? r.bw_dh_all + (int64_t)t * R * H : nullptr;
-  LaunchCtx::Scope sc(&cx, R >= 4096 ? "lstm_step_bwd" : "lstm_step_bwd_small", last ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
+  if (r.f16) {
+    const __half* g16 = r.gates16 + (int64_t)t * R * G;
+    __half* da16_t = r.da16 + (int64_t)t * R * G;
+    if (last) {
+      LaunchCtx::Scope sc(&cx, "lstm_step_bwd_last", 0.0, R * (2.0 * G + 2.0 * G + 16.0 * H));
+      lstm16_bwd_last(cx, R, H, g16, cp, r.c + (int64_t)t * R * H, r.bw_dh_last, r.scale2, mk, r.dc_carry, da16_t);
+    } else {
+      LaunchCtx::Scope sc(&cx, "lstm_step_bwd", 2.0 * R * G * H, R * (3.0 * 2.0 * G + 16.0 * H));
+      lstm16_step_bwd(cx, R, H, r.da16 + (int64_t)(t + 1) * R * G, r.Whb16, g16, cp, r.c + (int64_t)t * R * H, r.dc_carry, mk, da16_t);
+    }
+    return;
+  }
+  LaunchCtx::Scope sc(&cx, (last && r.bw_tc) ? "lstm_step_bwd_last" : (R >= 4096 ? "lstm_step_bwd" : "lstm_step_bwd_small"), last ? 0.0 : 2.0 * R * G * H, 4.0 * R * (2.0 * G + 5.0 * H));
   if (r.bw_tc) {
     // one fused kernel per step: dh_rec = da_{t+1} Wh on tcgen05, backward pointwise in the epilogue
     if (last) {         // no recurrent gradient yet: pointwise only (dh_last rides in the recurrent slot)
@@ -510,15 +573,21 @@ void Engine::lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float*
   const int64_t R = r.R, TR = (int64_t)r.T * R;
   const float* Ws = Wp(r.wseg);
   float* da = r.da;
+  if (r.f16) VD_REQUIRE(!dh0_out && !dc0_out && !dx_out && !r.h0, VD_E_STATE, "fp16 BPTT: no initial-state / input gradients");
   if (dh0_out) gemm_tn((int)R, H, G, da, G, nullptr, Ws + (int64_t)D * G, G, dh0_out, H, 0.f, nullptr, 0);
   if (dc0_out) VD_CUDA_CHECK(cudaMemcpyAsync(dc0_out, r.dc_carry, (size_t)R * H * sizeof(float), cudaMemcpyDeviceToDevice, cx.stream));
   // accGradParameters
   float* dWs = dWp(r.wseg);
   const float* A = r.x ? r.x : Wp(0);
   const int64_t lda = r.x ? D : cfg.E;
-  if (r.T > 1) gemm_atb(H, G, TR - R, r.h, H, nullptr, da + R * G, G, dWs + (int64_t)D * G, G);
+  if (r.f16) {
+    if (r.T > 1) {
+      LaunchCtx::Scope sc(&cx, "gemm_wgrad", 2.0 * H * G * (double)(TR - R), 2.0 * (double)(TR - R) * (H + G));
+      gemm_atb16(cx, H, G, TR - R, r.h16, H, r.da16 + R * G, G, dWs + (int64_t)D * G, G, r.scale2 + 1);
+    }
+  } else if (r.T > 1) gemm_atb(H, G, TR - R, r.h, H, nullptr, da + R * G, G, dWs + (int64_t)D * G, G);
   if (r.h0) gemm_atb(H, G, R, r.h0, H, nullptr, da, G, dWs + (int64_t)D * G, G);
-  if (!r.x && math_mode == VD_MATH_TF32) {
+  if (!r.x && tcmode()) {
     // Embedding-gathered input: every x_t is a row of the (V+1, E) table, so the three x-side gradients collapse
     // onto the table.  dP[v] = sum of da over the rows whose token is v (counting sort + balanced segmented sum,
     // HBM-bound) and then  dWx += E^T dP,  db += colsum(dP),  dEmb += dP Wx^T  are (V+1)-row contractions instead
@@ -531,9 +600,10 @@ void Engine::lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float*
     int32_t* perm = arena.get<int32_t>(TR);
     int32_t* stok = arena.get<int32_t>(TR);
     {
-      LaunchCtx::Scope sc(&cx, "embed_grad_segsum", 0.0, 4.0 * TR * G);
+      LaunchCtx::Scope sc(&cx, "embed_grad_segsum", 0.0, (r.f16 ? 2.0 : 4.0) * TR * G);
       group_rows_by_token(cx, r.gather, TR, V1, scratch, perm, stok);
-      segsum_rows(cx, da, G, perm, stok, TR, dP, G);
+      if (r.f16) segsum_rows16(cx, r.da16, G, perm, stok, TR, dP, G, r.scale2 + 1);
+      else segsum_rows(cx, da, G, perm, stok, TR, dP, G);
     }
     gemm_atb(D, G, V1, Wp(0), cfg.E, nullptr, dP, G, dWs, G);
     colsum_add(cx, dWp(r.wseg + 1), dP, V1, G, G);
@@ -561,7 +631,7 @@ void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2,
   const int H = l2.H, G = 4 * l2.H;
   const int64_t R = l2.R;
   float* dx2 = arena.get<float>((int64_t)l2.T * R * l2.D);      // = gradient wrt layer-1 outputs, all steps
-  const bool pipelined = math_mode == VD_MATH_TF32 && H % 128 == 0 && sb != nullptr && sb != sa && R >= wavefront_min_rows();
+  const bool pipelined = tcmode() && H % 128 == 0 && sb != nullptr && sb != sa && R >= wavefront_min_rows();
   const bool three = pipelined && sc != nullptr && sc != sa && sc != sb && three_streams_enabled();
   cx.stream = sa;
   if (!pipelined) {
@@ -1012,7 +1082,7 @@ void Engine::decoder_backward() {
       cx.stream = opt_stream;
       cx.sm_budget = cx.sm_count - opt_reserve_sms;
     }
-    if (math_mode == VD_MATH_TF32) {
+    if (tcmode()) {
       // embedding gradient in projected space; written to a private (V+1,E) buffer when overlapped, because the
       // encoder's embedding gradients accumulate into dW(wordEmbed) with atomics at the same time
       opt.demb_out = opt_overlap ? (opt_demb = arena.get<float>((int64_t)(cfg.V + 1) * E)) : nullptr;

@@ -65,7 +65,12 @@ struct LstmRun {
   float* da = nullptr; float* dc_carry = nullptr; float* dh_rec = nullptr;
   const float* bw_dh_all = nullptr; const float* bw_dh_last = nullptr; const float* bw_dc_last = nullptr;
   bool bw_tc = false;
-  const float* h_last() const { return h + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
+  // VD_MATH_F16 run state (lstm16.cu): fp16 h / activated gates / da and x-projection table, fp32 c; `h` and `gates` stay null
+  bool f16 = false;
+  __half *h16 = nullptr, *gates16 = nullptr, *da16 = nullptr, *P16 = nullptr, *Wh16 = nullptr, *Whb16 = nullptr;
+  float* h32_last = nullptr;         // fp32 copy of the last step's h (what the fp32 consumers of the run read)
+  float* scale2 = nullptr;           // device {s, 1/s}: power-of-two scale of the BPTT (chosen from max|dL/dh_T|)
+  const float* h_last() const { return f16 ? h32_last : h + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
   const float* c_last() const { return c + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
 };
 
@@ -94,6 +99,7 @@ struct Engine {
   int training = 1;
   uint64_t drop_seed = 1234, drop_iter = 0;
   int math_mode = VD_MATH_TF32;
+  bool tcmode() const { return math_mode != VD_MATH_FP32; }   // TF32 and F16 both run the dense contractions on tcgen05
   Arena arena;
   GrowBuf stage[9];
   DevBatch db;

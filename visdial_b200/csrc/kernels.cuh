@@ -2,6 +2,7 @@
 // (paths relative to /root/reference).  All tensors fp32 row-major; ids int32 (0 = pad).
 #pragma once
 #include <algorithm>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace vd {
@@ -131,4 +132,24 @@ bool lstm_step_fwd_tc(LaunchCtx& cx, int64_t R, int H, const float* h_prev, cons
 bool lstm_step_bwd_tc(LaunchCtx& cx, int64_t R, int H, const float* da_next, const float* Wh, const float* gsave,
                       const float* c_prev, const float* c_cur, const float* dh_ext, float* dc_carry, const int32_t* mask_ids,
                       float* da);
+}  // namespace vd
+
+namespace vd {
+// VD_MATH_F16 (lstm16.cu): SeqLSTM over many rows with fp16 operands / fp16 saved state, fp32 accumulation and cell state
+bool lstm16_shape_ok(int64_t R, int H);
+void lstm16_step_fwd(LaunchCtx& cx, int64_t R, int H, const __half* h_prev16, const __half* Wh16, const __half* ptable16,
+                     const int32_t* tok, const float* bias, const float* c_prev, const int32_t* mask_ids, __half* gates16,
+                     float* c_out, __half* h16_out, float* h32_out);
+void lstm16_step_bwd(LaunchCtx& cx, int64_t R, int H, const __half* da_next16, const __half* Whb16, const __half* gates16,
+                     const float* c_prev, const float* c_cur, float* dc_carry, const int32_t* mask_ids, __half* da16);
+void lstm16_first_step(LaunchCtx& cx, int64_t R, int H, const __half* ptable16, const int32_t* tok, const float* bias,
+                       const float* c_prev, const int32_t* mask_ids, __half* gates16, float* c_out, __half* h16_out, float* h32_out);
+void lstm16_bwd_last(LaunchCtx& cx, int64_t R, int H, const __half* gates16, const float* c_prev, const float* c_cur,
+                     const float* dh_last, const float* scale, const int32_t* mask_ids, float* dc_carry, __half* da16);
+void cvt_f32_to_f16(LaunchCtx& cx, __half* dst, int64_t ldd, const float* src, int64_t lds, int64_t rows, int cols);
+void pick_grad_scale(LaunchCtx& cx, const float* x, int64_t n, uint32_t* bits, float* scale2);
+void segsum_rows16(LaunchCtx& cx, const __half* X, int64_t ldx, const int32_t* perm, const int32_t* sorted_tok, int64_t n,
+                   float* out, int ncols, const float* inv_scale);
+void gemm_atb16(LaunchCtx& cx, int M, int N, int64_t K, const __half* A, int64_t lda, const __half* B, int64_t ldb, float* C,
+                int64_t ldc, const float* inv_scale);
 }  // namespace vd
