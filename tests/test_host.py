@@ -166,3 +166,41 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "QA-rounds/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 4
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["native_so_loaded"] == []                 # the reference process never loads the product library
+    assert line["cpu_baseline_batched"]["value"] > 0
+    assert line["config"]["dialogs_per_gpu"] == 1
+
+
+def test_bench_reference_arm_picks_threads_and_runs_other_configs():
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "C1", "--steps", "1",
+                          "--warmup", "1", "--no-batched"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["metric"].startswith("QA-rounds/sec lf-ques+gen") and line["value"] > 0
+    assert line["config"]["dialogs_per_gpu"] == 4 and line["warmup"] == 1
+    assert len(line["thread_sweep_qa_rounds_per_s"]) >= 1 and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_oracle_layout_twin_matches_the_engine():
+    """oracle/layout.py (numpy-only, used by the reference arm) == vd_layout_* / init_parameters of the product."""
+    import bench
+    from oracle import layout as OL
+    from visdial_b200 import engine as E
+    assert {k: bench.DEFAULTS[k] for k in E.DEFAULT_PARAMS} == E.DEFAULT_PARAMS
+    for enc, dec in [("lf-ques", "gen"), ("lf-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "disc"),
+                     ("mn-att-ques-im-hist", "gen")]:
+        p = small_params(enc, dec, numAttentionLayers=2 if "att" in enc else 1)
+        segs, n = E.layout(p)
+        osegs, on = OL.layout(p)
+        assert n == on and len(segs) == len(osegs)
+        for a, b in zip(segs, osegs):
+            assert (a.name, a.offset, a.rows, a.cols, a.init, a.fan_in) == (b.name, b.offset, b.rows, b.cols, b.init, b.fan_in)
+        assert np.array_equal(E.init_parameters(p, seed=5), OL.init_parameters(p, seed=5))
+    for name in bench.CONFIGS:
+        p = bench.config_params(name)
+        q = E.derive_flags(dict(p))
+        assert p == q
