@@ -17,8 +17,9 @@ function decoderNet.backwardConnect(enc, dec)                      -- gen.lua:45
   vd.check(vd.C.vd_backward_connect(dec.engine, g))
   return g[0]
 end
-function decoderNet.decoderConnect(dec)                            -- gen.lua:63-68: beam search only (out of scope)
-  error('decoderConnect: generate.lua beam search is outside the accelerated hot path')
+function decoderNet.decoderConnect(dec)                            -- gen.lua:63-68
+  -- the reference copies each layer's last output / cell into userPrevOutput / userPrevCell; vd_gen_decoder_step takes the
+  -- previous (h, c) explicitly (the device pointers vd_gen_decoder_step returned for the previous token), nothing to copy
 end
 
 return decoderNet

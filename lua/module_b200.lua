@@ -10,6 +10,8 @@ local function newHalf(kind, params, name)
   return setmetatable({kind = kind, params = params, name = name}, Half)
 end
 
+-- `cbatch` = the vd_batch cdata (`visdial_ffi.batch(b).c`); the caller keeps the table visdial_ffi.batch returned alive
+-- for the whole step (it anchors the converted host tensors the struct points into)
 function Half:forward(cbatch)                       -- encoder:forward(inputs) / decoder:forward(x), model.lua:297,313,329
   local out = ffi.new('const float*[1]')
   if self.kind == 'enc' then vd.check(vd.C.vd_encoder_forward(self.engine, cbatch, out))

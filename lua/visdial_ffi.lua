@@ -78,20 +78,33 @@ function M.params(p)
 end
 
 -- dataloader batch table (dataloader.lua:324-478) -> vd_batch.  Ids are IntTensors on the host
--- (`:int():contiguous()`); the engine stages them to the device itself.
+-- (`:int():contiguous()`); the engine stages them to the device itself.  The converted tensors are temporaries: only
+-- their data pointers go into the struct, so they are ANCHORED in the returned table (`keep`) — otherwise LuaJIT may
+-- collect them before vd_encoder_forward has copied them (any ffi.new in between can trigger a GC cycle).  The caller
+-- holds the returned table until the step's last call that reads the batch (criterion / backward) has returned.
 function M.batch(b)
   local c = ffi.new('vd_batch')
-  local function ip(t) return t and ffi.cast('const int32_t*', t:int():contiguous():data()) or nil end
+  local keep = {}
+  local function ip(t)
+    if not t then return nil end
+    local ti = t:int():contiguous()
+    keep[#keep + 1] = ti
+    return ffi.cast('const int32_t*', ti:data())
+  end
   c.B = b.ques_fwd:size(1); c.Tq = b.ques_fwd:size(3)
   c.ques_fwd = ip(b.ques_fwd)
   if b.hist then c.Th = b.hist:size(3); c.hist = ip(b.hist) end
-  if b.img_feat then c.img_feat = ffi.cast('const float*', b.img_feat:float():contiguous():data()) end
+  if b.img_feat then
+    local tf = b.img_feat:float():contiguous()
+    keep[#keep + 1] = tf
+    c.img_feat = ffi.cast('const float*', tf:data())
+  end
   if b.options then c.To = b.options:size(3); c.options = ip(b.options) end
   if b.answer_ind then c.answer_ind = ip(b.answer_ind) end
   if b.answer_in then c.Ta = b.answer_in:size(3); c.answer_in = ip(b.answer_in); c.answer_out = ip(b.answer_out) end
   if b.option_in then c.To = b.option_in:size(4); c.option_in = ip(b.option_in); c.option_out = ip(b.option_out) end
   c.on_device = 0
-  return c
+  return {c = c, keep = keep}
 end
 
 return M

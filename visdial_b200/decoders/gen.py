@@ -14,5 +14,9 @@ def backwardConnect(enc, dec):                     # gen.lua:45-60 -> gradient w
     return dec._eng().backward_connect(dec._last_batch)
 
 
-def decoderConnect(dec):                           # gen.lua:63-68 — only used by beam search (out of scope)
-    raise NotImplementedError("decoderConnect is used by generate.lua's beam search, outside the hot path")
+def decoderConnect(dec):                           # gen.lua:63-68
+    """The reference copies every decoder layer's last output / cell into userPrevOutput / userPrevCell so that the next
+    single-token forward continues the sequence.  Here the chaining is explicit: `vd_gen_decoder_step` takes the previous
+    (h, c) of both layers as arguments and `Model.generateAnswers` hands it the state the previous step returned, so
+    there is nothing left to copy."""
+    return None

@@ -16,6 +16,7 @@ DEFAULT_PARAMS = dict(
     imgFeatureSize=4096, imgSpatialSize=14, imgEmbedSize=300, commonEmbeddingSize=512,
     numAttentionLayers=1, maxQuesCount=10, numOptions=100, dropout=0.5, gpuid=0,
     batchSize=40, learningRate=1e-3, lrDecayRate=0.9997592083, minLRate=5e-5, useGt=True,
+    imgNorm=1,                                  # opts.lua:15; forced to 0 for 'att' encoders (opts.lua:66)
 )
 
 

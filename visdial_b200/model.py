@@ -1,7 +1,7 @@
 """Mirror of the reference's `Model` class (/root/reference/model.lua:8-430) over the C engine.
 Same method names, argument meaning and call order as the Lua original, so that the parity tests
-read like the reference's own driver code.  Beam search / sampling (model.lua:432-613) is out of
-scope."""
+read like the reference's own driver code.  `generateAnswers` (beam search / sampling, model.lua:432-613) steps the
+decoder on the device through vd_gen_decoder_step and keeps the hypothesis bookkeeping on the host like the Lua."""
 from __future__ import annotations
 
 import numpy as np
@@ -16,6 +16,15 @@ def _as_batch(b):
     if isinstance(b, tuple):
         b = b[0]
     return b if isinstance(b, Batch) else Batch(b)
+
+
+def _image_id(x):
+    """dataloader.lua:42-44: `tonumber(string.match(name, '000%d+'))` on the json image names; ints pass through."""
+    if isinstance(x, (int, np.integer)):
+        return int(x)
+    import re
+    mt = re.search(r"000\d+", str(x))
+    return int(mt.group(0)) if mt else x
 
 
 def _num_tokens(batch) -> int:
@@ -116,17 +125,52 @@ class Model:
                 numTokens += _num_tokens(batch)
             n += 1
         self.wrapper.training()
+        # :133 divides the summed loss by the answer-token count; for disc (a mean criterion per batch, no token count in
+        # the disc batch table) the mean over batches is the comparable figure
         return curLoss / max(numTokens, 1) if self.params["decoder"] == "gen" else curLoss / max(n, 1)
 
-    def retrieve(self, dataloader, dtype="val"):                           # model.lua:142-189
+    def _rank_walk(self, dataloader, dtype, use_gt):
+        """The getTestBatch loop shared by retrieve / predict (model.lua:153-166, :208-221)."""
         self.wrapper.evaluate()
-        ranks = []
+        out = []
         numThreads = dataloader.numThreads[dtype]
         for startId in range(0, numThreads, self.params["batchSize"]):
             batch = _as_batch(dataloader.getTestBatch(startId, self.params, dtype))
-            ranks.append(self.retrieveBatch(batch).reshape(-1, self.params["maxQuesCount"]))
+            out.append(self.engine.retrieve(batch, use_gt=use_gt))
         self.wrapper.training()
-        return np.concatenate(ranks, 0)
+        return out
+
+    def _round_table(self, dataloader, dtype, ranks, last_round_only):
+        """model.lua:175-185 / :227-243: one {image_id, round_id, ranks} entry per (dialog, round)."""
+        img = getattr(dataloader, "unique_img_" + dtype, None)
+        nr = getattr(dataloader, dtype + "_num_rounds", None)
+        first = dataloader.part[dtype][0] if dtype in getattr(dataloader, "part", {}) else 0
+        table = []
+        for i in range(ranks.shape[0]):
+            n_i = int(nr[first + i]) if nr is not None else ranks.shape[1]
+            iid = _image_id(img[first + i]) if img is not None else first + i
+            rounds = [n_i] if last_round_only else range(1, n_i + 1)
+            for j in rounds:
+                r = ranks[i, j - 1]
+                table.append({"image_id": iid, "round_id": int(j), "ranks": r.tolist() if np.ndim(r) else int(r)})
+        return table
+
+    def retrieve(self, dataloader, dtype="val", as_table=False, verbose=False):   # model.lua:142-189
+        """Ground-truth ranks of a split, (numThreads, maxQuesCount).  `as_table=True` returns what the reference returns:
+        the {image_id, round_id, ranks} list, after printing utils.processRanks of the matrix."""
+        use_gt = bool(self.params.get("useGt", True))
+        ranks = np.concatenate([r.reshape(-1, self.params["maxQuesCount"]) for r in self._rank_walk(dataloader, dtype, use_gt)], 0)
+        if not as_table:
+            return ranks
+        from .utils import processRanks
+        processRanks(ranks, verbose=verbose)                                       # :170
+        return self._round_table(dataloader, dtype, ranks, last_round_only=False)
+
+    def predict(self, dataloader, dtype="val"):                                   # model.lua:191-246
+        """Full 100-option rank lists (evaluate.lua's EvalAI dump): every round of a val dialog, the last round of a test one."""
+        K = int(self.params.get("numOptions", 100))
+        ranks = np.concatenate([r.reshape(-1, self.params["maxQuesCount"], K) for r in self._rank_walk(dataloader, dtype, False)], 0)
+        return self._round_table(dataloader, dtype, ranks, last_round_only=(dtype == "test"))
 
     # ---- beam search / sampling (model.lua:432-613, generate.lua) ---------------------------------------------
     def generateAnswers(self, dataloader, dtype="val", params=None, strict=True):
@@ -236,7 +280,9 @@ class Model:
                         threadAnswers.append(entry)
                 self.wrapper.training()                                                 # :605
                 img = getattr(dataloader, "unique_img_" + dtype, None)
-                answerTable.append({"image_id": img[convId] if img else convId, "dialog": threadAnswers})   # :606
+                # getIndexData hands out this rank's slice of the split: the image list is indexed by the global dialog id
+                gid = convId + (dataloader.part[dtype][0] if hasattr(dataloader, "part") and dtype in getattr(dataloader, "part", {}) else 0)
+                answerTable.append({"image_id": _image_id(img[gid]) if img is not None else gid, "dialog": threadAnswers})   # :606
         finally:
             for p in state_buf:
                 eng.device_free(p)
