@@ -22,17 +22,25 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, enc, dec, out):
+BIG = dict(rnnHiddenSize=256, embedSize=64, vocabSize=300, numOptions=100, commonEmbeddingSize=64, imgFeatureSize=64,
+           imgSpatialSize=4, imgEmbedSize=32)          # option LSTM: 2 dialogs x 10 x 100 = 2000 rows per rank -> tensor-core kernels
+
+
+def _case(enc, dec, mode, gpuid):
+    p = small_params(enc, dec, gpuid=gpuid, **(BIG if mode != 1 else {}))
+    return p, small_batch(p, B=4, seed=3)
+
+
+def _worker(rank, world, port, enc, dec, mode, out):
     import torch.distributed as dist
-    from visdial_b200 import VD_MATH_FP32, Batch, Engine, init_parameters
+    from visdial_b200 import Batch, Engine, init_parameters
     from visdial_b200 import dist as vdist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    p = small_params(enc, dec, gpuid=rank)
-    full = small_batch(p, B=4, seed=3)
+    p, full = _case(enc, dec, mode, rank)
     mine = vdist.shard_batch(full, rank, world, p["maxQuesCount"])
     eng = Engine(p)
-    eng.set_math_mode(VD_MATH_FP32)
+    eng.set_math_mode(mode)
     eng.set_parameters(init_parameters(p, seed=3))
     eng.set_training(2)                      # training graph, dropout off: masks are indexed per local shard
     vdist.attach_engine(eng, rank, world)
@@ -48,25 +56,28 @@ def _worker(rank, world, port, enc, dec, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("enc,dec", [("mn-att-ques-im-hist", "disc"), ("lf-ques", "gen")])
-def test_two_gpus_match_one(enc, dec):
+# mode 1 = fp32 (small shapes, CUDA-core kernels), 0 = TF32, 2 = F16: tensor-core kernels, option stream overlapped, and the
+# bucketed gradient all-reduce overlapped with the backward pass (the benched schedule)
+@pytest.mark.parametrize("enc,dec,mode", [("mn-att-ques-im-hist", "disc", 1), ("lf-ques", "gen", 1), ("mn-att-ques-im-hist", "disc", 2),
+                                          ("mn-att-ques-im-hist", "disc", 0), ("hrea-ques-im-hist", "gen", 0),
+                                          ("lf-ques-im-hist", "disc", 2)])
+def test_two_gpus_match_one(enc, dec, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    from visdial_b200 import VD_MATH_FP32, Batch, Engine, init_parameters
+    from visdial_b200 import Batch, Engine, init_parameters
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, enc, dec, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, enc, dec, mode, q)) for r in range(2)]
     for pr in procs:
         pr.start()
     w2, g2, losses = q.get(timeout=300)
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
-    p = small_params(enc, dec, gpuid=0)
-    full = small_batch(p, B=4, seed=3)
+    p, full = _case(enc, dec, mode, 0)
     eng = Engine(p)
-    eng.set_math_mode(VD_MATH_FP32)
+    eng.set_math_mode(mode)
     eng.set_parameters(init_parameters(p, seed=3))
     eng.set_training(2)
     eng.zero_grad()
@@ -79,5 +90,9 @@ def test_two_gpus_match_one(enc, dec):
     else:                                    # sum criterion: global loss = sum of the shard losses
         assert float(np.sum(losses)) == pytest.approx(loss1, rel=1e-5)
     scale = max(float(np.abs(g1).max()), 1e-30)
-    assert float(np.abs(g2 - g1).max()) < 1e-5 * scale + 1e-7
-    assert float(np.abs(w2 - w1).max()) < 0.02 * 1e-3            # Adam steps are ~lr: compare in units of lr
+    # fp32: reduction order only.  Tensor-core modes: the 1-GPU and 2-GPU runs tile the option rows differently and the
+    # fp16 BPTT picks its power-of-two scale per rank, so operand rounding differs at the 1e-3 level (stated TF32 class)
+    tol = 1e-5 if mode == 1 else 5e-3
+    assert float(np.abs(g2 - g1).max()) < tol * scale + 1e-7
+    if mode == 1:
+        assert float(np.abs(w2 - w1).max()) < 0.02 * 1e-3        # Adam steps are ~lr: compare in units of lr

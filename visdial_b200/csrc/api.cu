@@ -117,6 +117,13 @@ static void copy_out(Engine* e, float* dst, const float* src, int64_t n) {
   VD_REQUIRE(dst && n == e->nparams, VD_E_SHAPE, "n must equal vd_num_params");
   VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
   e->join_options_backward();
+  // with the overlapped gradient sync some buckets may already be all-reduced: finish the rest, so that what is read is
+  // always the complete global sum (never a mixture of local and reduced segments)
+  if (src == e->dW && e->world > 1) {
+    bool any = false;
+    for (char c : e->seg_reduced) any = any || c;
+    if (any) e->reduce_remaining();
+  }
   VD_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->cx.stream));
   VD_CUDA_CHECK(cudaStreamSynchronize(e->cx.stream));
 }
@@ -127,7 +134,9 @@ int vd_zero_grad(vd_engine* h) {
     Engine* e = ENG(h);
     VD_CUDA_CHECK(cudaSetDevice(e->cfg.gpuid));
     e->join_options_backward();
+    if (e->comm_pending) e->reduce_remaining();          // a reduction still in flight must not race the memset
     VD_CUDA_CHECK(cudaMemsetAsync(e->dW, 0, (size_t)e->nparams * sizeof(float), e->cx.stream));
+    e->arm_grad_sync();
   })
 }
 

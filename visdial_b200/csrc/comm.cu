@@ -69,15 +69,82 @@ void comm_init(Engine* e, const void* idbytes, int rank, int world) {
 }
 
 void comm_destroy(Engine* e) {
+  if (e->comm_stream) {
+    cudaStreamSynchronize(e->comm_stream);
+    cudaStreamDestroy(e->comm_stream); e->comm_stream = nullptr;
+    if (e->ev_comm_dep) cudaEventDestroy(e->ev_comm_dep);
+    if (e->ev_comm_done) cudaEventDestroy(e->ev_comm_done);
+    e->ev_comm_dep = e->ev_comm_done = nullptr;
+  }
   if (e->nccl_comm) { api().CommDestroy((ncclComm_t)e->nccl_comm); e->nccl_comm = nullptr; }
 }
 
-void Engine::allreduce_grads() {
+void Engine::arm_grad_sync() {
+  seg_reduced.assign(lay.segs.size(), 0);
+  ar_armed = world > 1 && ar_overlap && nccl_comm != nullptr;
+}
+
+// one ncclAllReduce(SUM) of dW[off, off+count) on the communication stream, ordered behind `producer` (or its event)
+void Engine::reduce_range(int64_t off, int64_t count, cudaStream_t producer, cudaEvent_t producer_event) {
+  VD_REQUIRE(nccl_comm != nullptr, VD_E_STATE, "communicator not initialised");
+  if (!comm_stream) {
+    int lo = 0, hi = 0;
+    VD_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VD_CUDA_CHECK(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, hi));
+    VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm_dep, cudaEventDisableTiming));
+    VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm_done, cudaEventDisableTiming));
+  }
+  if (!producer_event) {
+    VD_CUDA_CHECK(cudaEventRecord(ev_comm_dep, producer));
+    producer_event = ev_comm_dep;
+  }
+  VD_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, producer_event, 0));
+  cudaStream_t prev = cx.stream;
+  cx.stream = comm_stream;
+  {
+    LaunchCtx::Scope sc(&cx, "allreduce", 0.0, 2.0 * 4.0 * (double)count);
+    nccl_check(api().AllReduce(dW + off, dW + off, (size_t)count, ncclFloat32, ncclSum, (ncclComm_t)nccl_comm, comm_stream), "ncclAllReduce");
+  }
+  cx.stream = prev;
+  comm_pending = true;
+}
+
+void Engine::reduce_segments(int first, int last, cudaStream_t producer, cudaEvent_t producer_event) {
+  if (!ar_armed) return;
+  VD_REQUIRE(first >= 0 && last >= first && last < (int)lay.segs.size(), VD_E_STATE, "reduce_segments: range");
+  for (int i = first; i <= last; ++i) {
+    VD_REQUIRE(!seg_reduced[i], VD_E_STATE, "gradient bucket reduced twice");
+    seg_reduced[i] = 1;
+  }
+  const int64_t off = lay.segs[first].off;
+  const int64_t end = last + 1 < (int)lay.segs.size() ? lay.segs[last + 1].off : nparams;
+  reduce_range(off, end - off, producer, producer_event);
+}
+
+void Engine::reduce_remaining() {
   if (world <= 1) return;
   VD_REQUIRE(nccl_comm != nullptr, VD_E_STATE, "communicator not initialised");
   join_options_backward();
-  LaunchCtx::Scope sc(&cx, "allreduce", 0.0, 2.0 * 4.0 * (double)nparams);
-  nccl_check(api().AllReduce(dW, dW, (size_t)nparams, ncclFloat32, ncclSum, (ncclComm_t)nccl_comm, cx.stream), "ncclAllReduce");
+  if (seg_reduced.size() != lay.segs.size()) seg_reduced.assign(lay.segs.size(), 0);
+  const int n = (int)lay.segs.size();
+  for (int i = 0; i < n;) {
+    if (seg_reduced[i]) { ++i; continue; }
+    int j = i;
+    while (j + 1 < n && !seg_reduced[j + 1]) ++j;
+    for (int k = i; k <= j; ++k) seg_reduced[k] = 1;
+    const int64_t off = lay.segs[i].off;
+    const int64_t end = j + 1 < n ? lay.segs[j + 1].off : nparams;
+    reduce_range(off, end - off, main_stream, nullptr);
+    i = j + 1;
+  }
+  if (comm_pending) {
+    VD_CUDA_CHECK(cudaEventRecord(ev_comm_done, comm_stream));
+    VD_CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev_comm_done, 0));
+    comm_pending = false;
+  }
+  ar_armed = false;
 }
+
+void Engine::allreduce_grads() { reduce_remaining(); }
 
 }  // namespace vd

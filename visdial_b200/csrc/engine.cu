@@ -832,6 +832,10 @@ void Engine::encoder_backward(const float* dEnc) {
   float* dq3 = arena.get<float>(N * H);
   float* dh3 = cfg.useHist ? arena.get<float>(N * H) : nullptr;
   float* dpre = arena.get<float>(N * H);
+  // gradient sync, bucket 0: the decoder's own weights are final once decoder_backward is enqueued (gen: dec.lstm1/2 +
+  // dec.out, 20 MB at V = 10k; disc without the option stream: opt.lstm) — their all-reduce overlaps the whole encoder BPTT
+  if (cfg.dec == DEC_GEN) reduce_segments(seg("dec.lstm1.weight"), (int)lay.segs.size() - 1, main_stream);
+  else if (!opt_bwd_pending) reduce_segments(seg("opt.lstm.weight"), (int)lay.segs.size() - 1, main_stream);
 
   if (cfg.enc == ENC_LF_QUES || cfg.enc == ENC_LF_QIH) {
     tanh_bwd(cx, dpre, dEnc, encOut, N * H);
@@ -901,6 +905,8 @@ void Engine::encoder_backward(const float* dEnc) {
     dropout_apply(cx, dhAtt, dhAtt, N * H, d05, SITE_HATT);
     mn_attention_bwd(cx, q3, h3, probs, dhAtt, dq3, dh3, B, R, H);
     add_inplace(cx, dq3, dsum1, N * H);
+    // bucket 1: every non-recurrent layer of the encoder (mn.*, san.*) is final here, before the LSTM BPTTs start
+    reduce_segments(seg("mn.fact.weight"), seg("san.out.weight") + 1, main_stream);
   }
 
   // question LSTMs (+ gradients handed back by the gen decoder, gen.lua:45-60); the history chain's BPTT runs
@@ -910,6 +916,7 @@ void Engine::encoder_backward(const float* dEnc) {
     fork_side();
     float* dx1 = arena.get<float>(N * db.Th * E);
     lstm_pair_backward(hist1, hist2, dh3, nullptr, nullptr, nullptr, dx1, side_stream, side2_stream, side3_stream);
+    reduce_segments(seg("hist.lstm1.weight"), seg("hist.lstm2.weight") + 1, side_stream);       // bucket 2
     embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
     back_to_main();
   }
@@ -917,6 +924,7 @@ void Engine::encoder_backward(const float* dEnc) {
     int D1 = ques1.D;
     float* dx1 = arena.get<float>(N * db.Tq * D1);
     lstm_pair_backward(ques1, ques2, dq3, conn_dc_l2, conn_dh_l1, conn_dc_l1, dx1, main_stream, main2_stream, main3_stream);
+    reduce_segments(seg("ques.lstm1.weight"), seg("ques.lstm2.weight") + 1, main_stream);       // bucket 3
     embed_scatter_add(cx, dWp(0), dx1, D1, ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
     if (cfg.enc == ENC_HREA) {
       float* die = arena.get<float>(N * cfg.IE);
@@ -925,6 +933,10 @@ void Engine::encoder_backward(const float* dEnc) {
     }
   }
   join_side();
+  // bucket 4: the option LSTM's weights, behind the option stream's last kernel (issued last in host order so that it
+  // does not queue ahead of the encoder's buckets on the communication stream); what is left — the word embedding,
+  // which every branch writes, and the small layers not covered above — goes in clamp_adam_step
+  if (opt_bwd_pending) reduce_segments(seg("opt.lstm.weight"), (int)lay.segs.size() - 1, nullptr, ev_opt_done);
   join_options_backward();
 }
 
@@ -1065,6 +1077,9 @@ void Engine::criterion_backward() {
 
 void Engine::decoder_backward() {
   VD_REQUIRE(save_acts, VD_E_STATE, "decoder_backward needs a training-mode forward");
+  if (world > 1)
+    for (char c : seg_reduced)
+      VD_REQUIRE(!c, VD_E_STATE, "world > 1: vd_zero_grad is required between backward passes (gradients already all-reduced)");
   const int E = cfg.E, H = cfg.H, K = cfg.K;
   const int64_t N = db.N;
   dEncFromDec = arena.get<float>(N * H);

@@ -205,6 +205,19 @@ struct Engine {
   void gen_decoder_step(int64_t rows, const int32_t* tokens_host, const float* const* h_prev, const float* const* c_prev);
   void clamp_adam_step(float lr);
   void allreduce_grads();
+  // Overlapped gradient sync (world > 1): dW is all-reduced in buckets on `comm_stream` as soon as each bucket's last
+  // producer kernel is enqueued — decoder weights at the start of the encoder's backward, the encoder's non-recurrent
+  // layers after the attention stage, each LSTM pair after its BPTT, the option LSTM after its stream, the word embedding
+  // (the only segment every branch writes) last — instead of one all-reduce after the whole backward.  Armed by
+  // vd_zero_grad: a bucket is reduced at most once per zeroed gradient.
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_comm_dep = nullptr, ev_comm_done = nullptr;
+  std::vector<char> seg_reduced;
+  bool ar_overlap = true, ar_armed = false, comm_pending = false;
+  void reduce_range(int64_t off, int64_t count, cudaStream_t producer, cudaEvent_t producer_event);
+  void reduce_segments(int first, int last, cudaStream_t producer, cudaEvent_t producer_event = nullptr);
+  void reduce_remaining();           // everything not reduced yet, then main_stream waits for the communication stream
+  void arm_grad_sync();
 };
 
 }  // namespace vd
