@@ -196,6 +196,12 @@ Engine::~Engine() {
   if (opt_stream) cudaStreamSynchronize(opt_stream);
   arena.release();
   for (auto& g : stage) g.release();
+  if (copy_stream) {
+    cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream);
+    cudaEventDestroy(ev_img_ready); cudaEventDestroy(ev_copy_fork);
+    for (auto ev : ev_img_free) cudaEventDestroy(ev);
+  }
+  for (auto& g : stage_img) g.release();
   cudaFree(W); cudaFree(dW); cudaFree(m); cudaFree(v); cudaFree(Wt); cudaFree(scalars_dev); cudaFree(segtab_dev);
   if (flush_buf) cudaFree(flush_buf);
   cx.collect();
@@ -284,13 +290,46 @@ void Engine::stage_batch(const vd_batch* b) {
       {b->answer_out, (size_t)db.N * b->Ta * 4, (const void**)&db.answer_out},
       {b->option_in, (size_t)db.N * cfg.K * b->To * 4, (const void**)&db.option_in},
       {b->option_out, (size_t)db.N * cfg.K * b->To * 4, (const void**)&db.option_out}};
+  img_copy_pending = false;
   for (int i = 0; i < 9; ++i) {
     if (!items[i].src || items[i].bytes == 0) { *items[i].dst = nullptr; continue; }
     if (b->on_device) { *items[i].dst = items[i].src; continue; }
+    if (i == 2 && items[i].bytes >= ((size_t)1 << 20)) {
+      // image features: asynchronous copy on the copy stream into the staging buffer the previous step is not using
+      if (!copy_stream) {
+        VD_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_ready, cudaEventDisableTiming));
+        VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy_fork, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) VD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_img_free[k], cudaEventDisableTiming));
+      }
+      img_slot ^= 1;
+      if (items[i].bytes > stage_img[img_slot].cap) VD_CUDA_CHECK(cudaStreamSynchronize(copy_stream));   // growing frees the old block
+      void* d = stage_img[img_slot].ensure(items[i].bytes);
+      VD_CUDA_CHECK(cudaEventRecord(ev_copy_fork, cx.stream));                  // stream order behind whatever freed / allocated before
+      VD_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_copy_fork, 0));
+      if (img_free_recorded[img_slot]) VD_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_img_free[img_slot], 0));
+      VD_CUDA_CHECK(cudaMemcpyAsync(d, items[i].src, items[i].bytes, cudaMemcpyHostToDevice, copy_stream));
+      VD_CUDA_CHECK(cudaEventRecord(ev_img_ready, copy_stream));
+      img_copy_pending = true;
+      *items[i].dst = d;
+      continue;
+    }
     void* d = stage[i].ensure(items[i].bytes);
     VD_CUDA_CHECK(cudaMemcpyAsync(d, items[i].src, items[i].bytes, cudaMemcpyHostToDevice, cx.stream));
     *items[i].dst = d;
   }
+}
+
+void Engine::wait_img() {
+  if (!img_copy_pending) return;
+  VD_CUDA_CHECK(cudaStreamWaitEvent(cx.stream, ev_img_ready, 0));
+  if (cx.stream != main_stream) VD_CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev_img_ready, 0));   // later readers live on the main stream
+  img_copy_pending = false;
+}
+void Engine::release_img() {
+  if (!copy_stream || !db.img || db.img != stage_img[img_slot].p) return;
+  VD_CUDA_CHECK(cudaEventRecord(ev_img_free[img_slot], cx.stream));
+  img_free_recorded[img_slot] = true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -727,6 +766,7 @@ void Engine::encoder_forward(const vd_batch* b) {
   if (cfg.enc == ENC_HREA) {
     // hrea-ques-im-hist.lua:45-55: Dropout(0.5) -> Linear(F,IE) on the 10x repeated fc7, MaskTime, JoinTable(-1)
     img_d = arena.get<float>(N * cfg.F);
+    wait_img();
     repeat_rows(cx, img_d, db.img, B, R, cfg.F);
     dropout_apply(cx, img_d, img_d, N * cfg.F, d05, SITE_IMG_FC7);
     img_e = arena.get<float>(N * cfg.IE);
@@ -752,6 +792,7 @@ void Engine::encoder_forward(const vd_batch* b) {
     if (cfg.enc == ENC_LF_QIH) {
       // image repeated per round (model.lua:267-269), concat order [q | img | h]
       float* tmp = arena.get<float>(N * cfg.F);
+      wait_img();
       repeat_rows(cx, tmp, db.img, B, R, cfg.F);
       copy_cols(cx, join_d + H, joinK, tmp, cfg.F, N, cfg.F);
       copy_cols(cx, join_d + H + cfg.F, joinK, h3, H, N, H);
@@ -795,6 +836,7 @@ void Engine::encoder_forward(const vd_batch* b) {
     linear_fwd(seg("mn.query.weight"), sum1, N, qh2, 1);
     // SAN: tanh(Linear(img)) is computed once per dialog; Dropout then acts on the repeated tensor (:74-78)
     t_img = arena.get<float>((int64_t)B * P * H);
+    wait_img();
     linear_fwd(seg("san.img.weight"), db.img, (int64_t)B * P, t_img, 1);
     img_tr = arena.get<float>(N * P * H);
     san_expand_dropout(cx, img_tr, t_img, B, R, P, H, d05, SITE_IMG_TR);
@@ -819,6 +861,8 @@ void Engine::encoder_forward(const vd_batch* b) {
     dropout_apply(cx, u_d, u_hop[cfg.hops], N * H, d05, SITE_U_OUT);
     linear_fwd(seg("san.out.weight"), u_d, N, encOut, 1);
   }
+  wait_img();                // (an encoder that never reads the image still has to retire the copy before the buffer is reused)
+  release_img();             // forward-only callers never reach the backward's release; a later one simply overrides this
   have_fwd = true;
 }
 
@@ -895,6 +939,7 @@ void Engine::encoder_backward(const float* dEnc) {
     float* dt_pre = arena.get<float>((int64_t)B * P * H);
     san_collapse_bwd(cx, dimg_tr, t_img, dt_pre, B, R, P, H, d05, SITE_IMG_TR);
     linear_bwd(seg("san.img.weight"), db.img, dt_pre, (int64_t)B * P, nullptr, 0.f);
+    release_img();                                   // last reader of this step's image staging buffer
     // memory network part, :48-65
     tanh_bwd(cx, dpre, du, qh2, N * H);
     float* dsum1 = arena.get<float>(N * H);

@@ -102,6 +102,16 @@ struct Engine {
   bool tcmode() const { return math_mode != VD_MATH_FP32; }   // TF32 and F16 both run the dense contractions on tcgen05
   Arena arena;
   GrowBuf stage[9];
+  // The image features are 80 % of a host batch (12.8 MB of pool5 at B = 32) and are not needed until the attention stage:
+  // they are copied on their own stream into one of two staging buffers while the LSTM chains already run, and the
+  // consuming stream waits for the copy at the first use (wait_img).  ev_img_free[k] = last reader of buffer k done.
+  GrowBuf stage_img[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_img_ready = nullptr, ev_img_free[2] = {nullptr, nullptr}, ev_copy_fork = nullptr;
+  int img_slot = 0;
+  bool img_copy_pending = false, img_free_recorded[2] = {false, false};
+  void wait_img();                   // cx.stream waits for the asynchronous image copy (no-op once consumed)
+  void release_img();                // records "this step's last read of the image staging buffer" on cx.stream
   DevBatch db;
   float* scalars_dev = nullptr;      // [0] loss
   float* flush_buf = nullptr; int64_t flush_n = 0;

@@ -135,9 +135,14 @@ struct Lstm16Maps { CUtensorMap g16, c, h16; };   // [R,4H] fp16 gates / da ; [R
 // MODE 0 = forward step, MODE 1 = backward step.  2-CTA clusters, persistent over the tile list.
 template <int MODE>
 struct Cfg16 {
-  static constexpr int STG_PER_WARP = MODE == 0 ? (4 * S32_BYTES + S64_BYTES + S32_BYTES) : (4 * S32_BYTES + 3 * S64_BYTES);
-  static constexpr int STG_BYTES = EW16 * STG_PER_WARP;
-  static constexpr int STAGES = (232448 - 1024 - 256 - STG_BYTES) / STAGE16;      // fwd 5, bwd 4
+  // forward: TWO ping-pong buffers per warp, each {4 gate tiles S32, c tile S64, h tile S32} = 7 KB: the inputs of group
+  // g+1 are in flight (cp.async) while group g is computed; outputs overwrite the inputs in place and leave by TMA.
+  // backward: one buffer {4 gate tiles S32, c_prev, c_t, dc S64}.
+  static constexpr int BUF_BYTES = MODE == 0 ? (4 * S32_BYTES + S64_BYTES + S32_BYTES) : (4 * S32_BYTES + 3 * S64_BYTES);
+  static constexpr int STG_PER_WARP = MODE == 0 ? 2 * BUF_BYTES : BUF_BYTES;
+  static constexpr int BIAS_BYTES = MODE == 0 ? 4 * 512 * 4 : 0;                     // fp32 bias of all 4H gate columns (H <= 512)
+  static constexpr int STG_BYTES = EW16 * STG_PER_WARP + BIAS_BYTES;
+  static constexpr int STAGES = (232448 - 1024 - 256 - STG_BYTES) / STAGE16;      // fwd 3, bwd 4
   static constexpr int TOTAL = STAGES * STAGE16 + STG_BYTES + 1024 + 256;
 };
 
@@ -241,62 +246,92 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     uint8_t* stg = stg_all + (warp - 2) * C::STG_PER_WARP;
-    int it = 0;
-    for (int tile = cta; tile < num_tiles; tile += ncta, ++it) {
-      const int buf = it & 1;
-      const uint32_t bph = (it >> 1) & 1;
-      const int m0 = (tile / num_n) * 2 * BM16 + (int)rank * BM16;
-      const int nt = tile % num_n;
-      const int64_t row = (int64_t)m0 + q * 32 + lane;
-      const bool row_ok = row < p.R;
-      const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
-      const float keep = masked ? 0.f : 1.f;
-      const int r0 = m0 + q * 32;
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-
-      if (MODE == 0) {
-        // ---- forward: 64 hidden units per tile, this warp takes 32 of them in two groups of 16
-        const int j0 = nt * 64 + half * 32;
-        const __half* prow = row_ok ? p.ptable + (int64_t)p.tok[row] * 4 * H : nullptr;
-        const float* cprow = (row_ok && p.c_prev) ? p.c_prev + row * H : nullptr;
-        uint8_t* sG = stg; uint8_t* sC = stg + 4 * S32_BYTES; uint8_t* sH = sC + S64_BYTES;
-        bool waited = false;
-#pragma unroll 1
-        for (int grp = 0; grp < 2; ++grp) {
-          const int j = j0 + grp * 16;                 // first hidden unit of the group
-          const int tc0 = half * 32 + grp * 16;        // its column inside a gate block of the accumulator
-          if (lane == 0) bulk_wait_read0();            // the previous group's TMA stores have read the staging tiles
-          __syncwarp();
+    if constexpr (MODE == 0) {
+      // ---- forward.  64 hidden units per tile; this warp takes 32 of them in two groups of 16.  The groups of all tiles
+      // form one sequence g = 0, 1, 2, ...; group g lives in staging buffer g & 1: while it is computed the inputs of group
+      // g+1 (x-projection rows gathered from the fp16 table, previous cell) are already in flight into the other buffer.
+      float* sBias = reinterpret_cast<float*>(stg_all + EW16 * C::STG_PER_WARP);
+      for (int i = (int)threadIdx.x - 64; i < 4 * H; i += 32 * EW16) sBias[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW16) : "memory");          // epilogue warps only
+      auto tile_row = [&](int tile) { return (int64_t)(tile / num_n) * 2 * BM16 + (int64_t)rank * BM16 + q * 32 + lane; };
+      auto tok_of = [&](int tile) {
+        const int64_t r = tile_row(tile);
+        return (tile < num_tiles && r < p.R) ? __ldg(p.tok + r) : 0;
+      };
+      auto issue_loads = [&](int tile, int grp, int bsel, int32_t tk) {
+        const int64_t row = tile_row(tile);
+        const bool ok = row < p.R;
+        const int j = (tile % num_n) * 64 + half * 32 + grp * 16;
+        const __half* prow = ok ? p.ptable + (int64_t)tk * 4 * H + j : nullptr;
+        const float* cprow = (ok && p.c_prev) ? p.c_prev + row * H + j : nullptr;
+        uint8_t* b = stg + bsel * C::BUF_BYTES;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) s32_load(sG + g * S32_BYTES, prow ? prow + g * H + j : nullptr, lane);
-          s64_load(sC, cprow ? cprow + j : nullptr, lane);
-          if (!waited) { mbar_wait(&tfull[buf], bph); tc_fence_after(); waited = true; }   // loads fly while the MMAs finish
-          cp_wait_all();
+        for (int g = 0; g < 4; ++g) s32_load(b + g * S32_BYTES, prow ? prow + g * H : nullptr, lane);
+        s64_load(b + 4 * S32_BYTES, cprow, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int it = 0, gi = 0;
+      int32_t tokc = tok_of(cta);
+      if (cta < num_tiles) issue_loads(cta, 0, 0, tokc);
+      for (int tile = cta; tile < num_tiles; tile += ncta, ++it) {
+        const int buf = it & 1;
+        const uint32_t bph = (it >> 1) & 1;
+        const int next_tile = tile + ncta;
+        const int32_t tokn = tok_of(next_tile);                   // used one group later: its latency is hidden
+        const int m0 = (tile / num_n) * 2 * BM16 + (int)rank * BM16;
+        const int nt = tile % num_n;
+        const int64_t row = (int64_t)m0 + q * 32 + lane;
+        const bool row_ok = row < p.R;
+        const float keep = (row_ok && p.mask_ids && p.mask_ids[row] == 0) ? 0.f : 1.f;
+        const int r0 = m0 + q * 32;
+        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int grp = 0; grp < 2; ++grp, ++gi) {
+          const int bsel = gi & 1;
+          uint8_t* sG = stg + bsel * C::BUF_BYTES; uint8_t* sC = sG + 4 * S32_BYTES; uint8_t* sH = sC + S64_BYTES;
+          const int j = nt * 64 + half * 32 + grp * 16;          // first hidden unit of the group
+          const int tc0 = half * 32 + grp * 16;                  // its column inside a gate block of the accumulator
+          const bool have_next = grp == 0 || next_tile < num_tiles;
+          if (have_next) {
+            if (lane == 0) bulk_wait_read0();                    // the other buffer's TMA stores (previous group) have read it
+            __syncwarp();
+            if (grp == 0) issue_loads(tile, 1, bsel ^ 1, tokc); else issue_loads(next_tile, 0, bsel ^ 1, tokn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this group's inputs have landed
+          } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+          }
+          __syncwarp();
+          if (grp == 0) { mbar_wait(&tfull[buf], bph); tc_fence_after(); }
+          float acc[2][4][8];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * 64 + tc0 + sub * 8, acc[sub][g]);
+          tmem_ld_wait();
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            float a[4][8], cp[8], cn[8], hn[8];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * 64 + tc0 + sub * 8, a[g]);
-            tmem_ld_wait();
+            float cp[8], cn[8], hn[8];
             s64_get8(sC, lane, sub, cp);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float x[8];
               unpack8(*s32_at(sG + g * S32_BYTES, lane, sub), x);
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + g * H + j + sub * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + g * H + j + sub * 8) + 1);
-              a[g][0] += x[0] + b0.x; a[g][1] += x[1] + b0.y; a[g][2] += x[2] + b0.z; a[g][3] += x[3] + b0.w;
-              a[g][4] += x[4] + b1.x; a[g][5] += x[5] + b1.y; a[g][6] += x[6] + b1.z; a[g][7] += x[7] + b1.w;
+              const float4 b0 = *reinterpret_cast<const float4*>(sBias + g * H + j + sub * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBias + g * H + j + sub * 8 + 4);
+              float* a = acc[sub][g];
+              a[0] += x[0] + b0.x; a[1] += x[1] + b0.y; a[2] += x[2] + b0.z; a[3] += x[3] + b0.w;
+              a[4] += x[4] + b1.x; a[5] += x[5] + b1.y; a[6] += x[6] + b1.z; a[7] += x[7] + b1.w;
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float gi = fsigmoid(a[0][e]), gf = fsigmoid(a[1][e]), go = fsigmoid(a[2][e]), gg = ftanh(a[3][e]);
-              const float c_ = gf * cp[e] + gi * gg;
-              a[0][e] = gi * keep; a[1][e] = gf * keep; a[2][e] = go * keep; a[3][e] = gg * keep;
+              const float gi_ = fsigmoid(acc[sub][0][e]), gf = fsigmoid(acc[sub][1][e]), go = fsigmoid(acc[sub][2][e]),
+                          gg = ftanh(acc[sub][3][e]);
+              const float c_ = gf * cp[e] + gi_ * gg;
+              acc[sub][0][e] = gi_ * keep; acc[sub][1][e] = gf * keep; acc[sub][2][e] = go * keep; acc[sub][3][e] = gg * keep;
               cn[e] = c_ * keep; hn[e] = go * ftanh(c_) * keep;
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *s32_at(sG + g * S32_BYTES, lane, sub) = pack8(a[g]);
+            for (int g = 0; g < 4; ++g) *s32_at(sG + g * S32_BYTES, lane, sub) = pack8(acc[sub][g]);
             s64_put8(sC, lane, sub, cn);
             *s32_at(sH, lane, sub) = pack8(hn);
             if (p.h32_out && row_ok) {                  // last step only: the fp32 h that meets the encoder output
@@ -318,7 +353,28 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           }
           __syncwarp();
         }
-      } else {
+        tokc = tokn;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                // the accumulator buffer may be overwritten by the leader's MMAs
+          if (!leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
+          else mbar_arrive(&tempty[buf]);
+        }
+      }
+    } else {
+    int it = 0;
+    for (int tile = cta; tile < num_tiles; tile += ncta, ++it) {
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      const int m0 = (tile / num_n) * 2 * BM16 + (int)rank * BM16;
+      const int nt = tile % num_n;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const bool row_ok = row < p.R;
+      const bool masked = row_ok && p.mask_ids && p.mask_ids[row] == 0;
+      const float keep = masked ? 0.f : 1.f;
+      const int r0 = m0 + q * 32;
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      {
         // ---- backward: 256 hidden units per tile, this warp takes 128 of them in eight groups of 16
         const int j0 = nt * 256 + half * 128;
         const __half* grow = row_ok ? p.gsave + row * 4 * H : nullptr;
@@ -383,6 +439,7 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         if (!leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
         else mbar_arrive(&tempty[buf]);
       }
+    }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores performed
   }
@@ -717,7 +774,7 @@ static void launch16(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB
 
 }  // namespace tc
 
-bool lstm16_shape_ok(int64_t R, int H) { return H % 256 == 0 && R >= 1024; }
+bool lstm16_shape_ok(int64_t R, int H) { return H % 256 == 0 && H <= 512 && R >= 1024; }   // the forward kernel keeps the 4H bias in 8 KB of shared memory
 
 void lstm16_step_fwd(LaunchCtx& cx, int64_t R, int H, const __half* h_prev16, const __half* Wh16, const __half* ptable16,
                      const int32_t* tok, const float* bias, const float* c_prev, const int32_t* mask_ids, __half* gates16,

@@ -94,7 +94,7 @@ class Corpus:
         d.concatHistory = int(bool(opt.get("concatHistory")))
         d.useIm = int(bool(opt.get("useIm")))
         d.maxHistoryLen = int(opt.get("maxHistoryLen") or 60)                       # dataloader.lua:142
-        d.imgNorm = 0 if "att" in opt.get("encoder", "") else int(opt.get("imgNorm", 1))   # opts.lua:15,66; dataloader.lua:63-67
+        d.imgNorm = int(opt.get("imgNorm", 1))          # opts.lua:15 default 1; opts.lua:66 (derive_flags) sets 0 for 'att' encoders
         att = "att" in opt.get("encoder", "")                                       # :70
         d.imgAtt = int(att)
         if d.useIm:
