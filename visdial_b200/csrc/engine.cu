@@ -498,7 +498,35 @@ static bool three_streams_enabled() {
   return v == 1;
 }
 
+static bool enc_persist_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VD_ENC_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) {
+  // VD_MATH_F16: both layers and all time steps in ONE persistent launch (enc_lstm.cu) — weight slices stationary in
+  // shared memory, steps chained through global flags — instead of 3 launches per time step on three streams
+  if (math_mode == VD_MATH_F16 && enc_persist_enabled() && !l1.h0 && !l1.c0 && !l2.h0 && !l2.c0 && !l1.gather && l1.x &&
+      l1.H == l2.H && l2.D == l1.H && l1.R == l2.R && l1.T == l2.T && l1.mask == l2.mask && enc_pair_shape_ok(l1.R, l1.H, cx.sm_count)) {
+    const int H = l1.H, G = 4 * H, T = l1.T;
+    const int64_t R = l1.R;
+    cx.stream = sa;
+    lstm_forward_begin(l1, true);               // h / c / gates of layer 1; gates1 <- x-projection + bias (batched GEMM)
+    l2.x = l1.h;
+    l2.step_xproj = true;                       // no batched x-projection for layer 2: it is part of the fused K = 2H contraction
+    lstm_forward_begin(l2, true);
+    l1.h16 = arena.get<__half>((int64_t)T * R * H);
+    l2.h16 = arena.get<__half>((int64_t)T * R * H);
+    __half* W1h = arena.get<__half>((int64_t)G * H);
+    __half* W2c = arena.get<__half>((int64_t)G * 2 * H);
+    cvt_f32_to_f16(cx, W1h, H, Wtp(l1.wseg) + l1.D, l1.D + H, G, H);                   // [4H, H]   recurrent block of layer 1
+    cvt_f32_to_f16(cx, W2c, 2 * H, Wtp(l2.wseg), 2 * H, G, 2 * H);                     // [4H, 2H]  [Wx2 | Wh2] of layer 2
+    int* flags = arena.get<int>(2 * (int64_t)cdiv(R, 128) * T);
+    LaunchCtx::Scope sc2(&cx, "enc_pair_fwd", 2.0 * T * R * G * 3.0 * H, 4.0 * T * R * (2.0 * G + 2.0 * G + 6.0 * H));
+    enc_pair_forward(cx, T, R, H, W1h, W2c, Wp(l2.wseg + 1), l1.mask, l1.gates, l1.c, l1.h, l1.h16, l2.gates, l2.c, l2.h, l2.h16, flags);
+    return;
+  }
   const bool pipelined = tcmode() && l2.H % 64 == 0 && sb != nullptr && sb != sa && l2.R >= wavefront_min_rows();
   const bool three = pipelined && sc != nullptr && sc != sa && sc != sb && three_streams_enabled();
   cx.stream = sa;

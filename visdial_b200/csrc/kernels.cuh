@@ -152,4 +152,9 @@ void segsum_rows16(LaunchCtx& cx, const __half* X, int64_t ldx, const int32_t* p
                    float* out, int ncols, const float* inv_scale);
 void gemm_atb16(LaunchCtx& cx, int M, int N, int64_t K, const __half* A, int64_t lda, const __half* B, int64_t ldb, float* C,
                 int64_t ldc, const float* inv_scale);
+// persistent two-layer SeqLSTM of the few-row encoder LSTMs (enc_lstm.cu): one launch for both layers and all T steps
+bool enc_pair_shape_ok(int64_t R, int H, int sm_count);
+void enc_pair_forward(LaunchCtx& cx, int T, int64_t R, int H, const __half* W1h16, const __half* W2cat16, const float* bias2,
+                      const int32_t* mask, float* gates1, float* c1, float* h1, __half* h1_16, float* gates2, float* c2, float* h2,
+                      __half* h2_16, int* flags);
 }  // namespace vd
