@@ -213,12 +213,32 @@ k_enc_pair_fwd(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__
         const bool has_acc = layer == 1 || t > 0;
         const int64_t tr = (int64_t)t * p.R + row;
         const float keep = (row_ok && p.mask && p.mask[tr] == 0) ? 0.f : 1.f;
-        if (has_acc) { mbar_wait(tfull, nuse & 1); tc_fence_after(); ++nuse; }
         const int nsub = HS / 8;
+        // additive term of the pre-activation: layer 1 = this step's x-projection (+ bias) rows, layer 2 = the bias.  The
+        // loads of sub-tile s+1 are issued before the math of sub-tile s, those of sub-tile 0 before the accumulator is awaited.
+        float xn[4][8];
+        auto load_x = [&](int sub) {
+          const int j = j0 + sub * 8;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (!row_ok) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) xn[g][e] = 0.f;
+            } else if (layer == 0) ld8g(gates + tr * 4 * H + g * H + j, xn[g]);
+            else ld8g(p.bias2 + g * H + j, xn[g]);
+          }
+        };
+        load_x(0);
+        if (layer == 0 && row_ok && t + 1 < T) {             // next step's x-projection rows: pull them into L2 now
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gates + (tr + p.R) * 4 * H + g * H + j0) : "memory");
+        }
+        if (has_acc) { mbar_wait(tfull, nuse & 1); tc_fence_after(); ++nuse; }
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
           if (sub < nsub) {
-            float a[4][8], x[8], hn[8];
+            float a[4][8], hn[8];
             if (has_acc) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * HS + sub * 8, a[g]);
@@ -229,28 +249,26 @@ k_enc_pair_fwd(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a[g][e] = 0.f;
             }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[g][e] += xn[g][e];
+            if (sub + 1 < nsub) load_x(sub + 1);
             const int j = j0 + sub * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float gi = fsigmoid(a[0][e]), gf = fsigmoid(a[1][e]), go = fsigmoid(a[2][e]), gg = ftanh(a[3][e]);
+              const float c_ = (gf * c[sub * 8 + e] + gi * gg) * keep;       // maskzero: state reset on an all-zero input row
+              a[0][e] = gi * keep; a[1][e] = gf * keep; a[2][e] = go * keep; a[3][e] = gg * keep;
+              c[sub * 8 + e] = c_;
+              hn[e] = go * ftanh(c_) * keep;
+            }
             if (row_ok) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (layer == 0) ld8g(gates + tr * 4 * H + g * H + j, x);          // x-projection (+ bias) of this step
-                else ld8g(p.bias2 + g * H + j, x);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[g][e] += x[e];
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float gi = fsigmoid(a[0][e]), gf = fsigmoid(a[1][e]), go = fsigmoid(a[2][e]), gg = ftanh(a[3][e]);
-                const float c_ = (gf * c[sub * 8 + e] + gi * gg) * keep;       // maskzero: state reset on an all-zero input row
-                a[0][e] = gi * keep; a[1][e] = gf * keep; a[2][e] = go * keep; a[3][e] = gg * keep;
-                c[sub * 8 + e] = c_;
-                hn[e] = go * ftanh(c_) * keep;
-              }
+              *reinterpret_cast<uint4*>(h16 + tr * H + j) = ep_pack8(hn);   // what the next step's TMA reads goes out first
 #pragma unroll
               for (int g = 0; g < 4; ++g) st8g(gates + tr * 4 * H + g * H + j, a[g]);
               st8g(cst + tr * H + j, &c[sub * 8]);
               st8g(hst + tr * H + j, hn);
-              *reinterpret_cast<uint4*>(h16 + tr * H + j) = ep_pack8(hn);
             }
           }
         }
@@ -259,10 +277,13 @@ k_enc_pair_fwd(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty);
         }
-        // publish step t of this slice: every thread's stores are fenced, then one thread counts the slice in
-        __threadfence();
+        // publish step t of this slice: CTA barrier, then ONE gpu-scope fence (cumulative over what the barrier made
+        // visible to the signalling thread) and the count-in — the grid-sync idiom of cooperative groups
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) atomicAdd(flag + (size_t)rb * T + t, 1);
+        if (threadIdx.x == 64) {
+          __threadfence();
+          atomicAdd(flag + (size_t)rb * T + t, 1);
+        }
       }
     }
   }

@@ -787,7 +787,13 @@ void Engine::encoder_forward(const vd_batch* b) {
   auto run_two = [&](LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) { lstm_pair_forward(l1, l2, sa, sb, sc); };
   // The history and question LSTM chains are independent until the fusion/attention stage: the history chain runs
   // on the side stream (its tiny per-step kernels are latency-bound; overlapping the two chains hides half of it).
-  if (cfg.useHist) { fork_side(); run_two(hist1, hist2, side_stream, side2_stream, side3_stream); back_to_main(); }
+  // (the persistent pair kernels of VD_MATH_F16 are flag-chained grids that want every SM: two of them must never be
+  //  co-scheduled — neither could become fully resident — so in that mode both pairs run on the main stream, in order)
+  const bool serial_pairs = math_mode == VD_MATH_F16 && enc_persist_enabled();
+  if (cfg.useHist) {
+    if (serial_pairs) { join_side(); run_two(hist1, hist2, main_stream, main2_stream, main3_stream); }
+    else { fork_side(); run_two(hist1, hist2, side_stream, side2_stream, side3_stream); back_to_main(); }
+  }
   // question branch
   xq = arena.get<float>(N * db.Tq * E);
   embed_rows(cx, xq, Wp(0), ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);

@@ -27,8 +27,9 @@ namespace tc {
 constexpr int BM16 = 128;        // rows per CTA (UMMA M = 256 per pair)
 constexpr int BK16 = 64;         // halves per k-block = one 128-byte swizzle row
 constexpr int UK16 = 16;         // kind::f16: 32 bytes per instruction
-constexpr int EW16 = 8;          // epilogue warps
-constexpr int THREADS16 = 64 + 32 * EW16;
+// epilogue warps: 16 forward (four per TMEM lane quarter, one 16-unit column group each: the pointwise half is
+// instruction-issue / latency bound, and four warps per scheduler hide what two could not), 8 backward (HBM-bound)
+template <int MODE> struct EW16T { static constexpr int N = MODE == 0 ? 16 : 8; };
 constexpr int STAGE16 = 32768;   // 16 KB of A (this CTA's 128 rows) + 16 KB of B (this CTA's half of the 256-column tile)
 
 // instruction descriptor, kind::f16: D = f32 (c_format 1), A = B = f16 (format 0)
@@ -46,6 +47,13 @@ __device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, ui
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+
+// sigmoid / tanh as {FMUL, MUFU.EX2, FADD, MUFU.RCP [, FFMA]}: abs error ~1e-7 like fsigmoid / ftanh of tc_ptx.cuh, without the
+// range fix-ups of __fdividef / copysign (ex2 -> +inf gives rcp -> 0, ex2 -> 0 gives 1: both limits are exact)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sig16(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh16(float x) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f); }
 
 // ---- fp16 <-> fp32 packing (round to nearest even, saturating: a scaled gradient that outgrows the range clamps to
 // +-65504 instead of becoming inf)
@@ -135,19 +143,19 @@ struct Lstm16Maps { CUtensorMap g16, c, h16; };   // [R,4H] fp16 gates / da ; [R
 // MODE 0 = forward step, MODE 1 = backward step.  2-CTA clusters, persistent over the tile list.
 template <int MODE>
 struct Cfg16 {
-  // forward: TWO ping-pong buffers per warp, each {4 gate tiles S32, c tile S64, h tile S32} = 7 KB: the inputs of group
-  // g+1 are in flight (cp.async) while group g is computed; outputs overwrite the inputs in place and leave by TMA.
-  // backward: one buffer {4 gate tiles S32, c_prev, c_t, dc S64}.
-  static constexpr int BUF_BYTES = MODE == 0 ? (4 * S32_BYTES + S64_BYTES + S32_BYTES) : (4 * S32_BYTES + 3 * S64_BYTES);
-  static constexpr int STG_PER_WARP = MODE == 0 ? 2 * BUF_BYTES : BUF_BYTES;
+  static constexpr int EW = EW16T<MODE>::N;
+  static constexpr int THREADS = 64 + 32 * EW;
+  // per-warp staging: forward {4 gate tiles S32, c tile S64, h tile S32} = 7 KB (inputs land here by cp.async, outputs
+  // overwrite them in place and leave by TMA); backward {4 gate tiles S32, c_prev, c_t, dc S64} = 10 KB
+  static constexpr int STG_PER_WARP = MODE == 0 ? (4 * S32_BYTES + S64_BYTES + S32_BYTES) : (4 * S32_BYTES + 3 * S64_BYTES);
   static constexpr int BIAS_BYTES = MODE == 0 ? 4 * 512 * 4 : 0;                     // fp32 bias of all 4H gate columns (H <= 512)
-  static constexpr int STG_BYTES = EW16 * STG_PER_WARP + BIAS_BYTES;
+  static constexpr int STG_BYTES = EW * STG_PER_WARP + BIAS_BYTES;
   static constexpr int STAGES = (232448 - 1024 - 256 - STG_BYTES) / STAGE16;      // fwd 3, bwd 4
   static constexpr int TOTAL = STAGES * STAGE16 + STG_BYTES + 1024 + 256;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(THREADS16, 1)
+__global__ void __launch_bounds__(Cfg16<MODE>::THREADS, 1)
 k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
          const __grid_constant__ Lstm16Maps em, const Lstm16Params p) {
   using C = Cfg16<MODE>;
@@ -174,7 +182,7 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EW16 * 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], C::EW * 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster_sync_all();
@@ -247,119 +255,84 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int half = (warp - 2) >> 2;
     uint8_t* stg = stg_all + (warp - 2) * C::STG_PER_WARP;
     if constexpr (MODE == 0) {
-      // ---- forward.  64 hidden units per tile; this warp takes 32 of them in two groups of 16.  The groups of all tiles
-      // form one sequence g = 0, 1, 2, ...; group g lives in staging buffer g & 1: while it is computed the inputs of group
-      // g+1 (x-projection rows gathered from the fp16 table, previous cell) are already in flight into the other buffer.
-      float* sBias = reinterpret_cast<float*>(stg_all + EW16 * C::STG_PER_WARP);
-      for (int i = (int)threadIdx.x - 64; i < 4 * H; i += 32 * EW16) sBias[i] = __ldg(p.bias + i);
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW16) : "memory");          // epilogue warps only
-      auto tile_row = [&](int tile) { return (int64_t)(tile / num_n) * 2 * BM16 + (int64_t)rank * BM16 + q * 32 + lane; };
-      auto tok_of = [&](int tile) {
-        const int64_t r = tile_row(tile);
-        return (tile < num_tiles && r < p.R) ? __ldg(p.tok + r) : 0;
-      };
-      auto issue_loads = [&](int tile, int grp, int bsel, int32_t tk) {
-        const int64_t row = tile_row(tile);
-        const bool ok = row < p.R;
-        const int j = (tile % num_n) * 64 + half * 32 + grp * 16;
-        const __half* prow = ok ? p.ptable + (int64_t)tk * 4 * H + j : nullptr;
-        const float* cprow = (ok && p.c_prev) ? p.c_prev + row * H + j : nullptr;
-        uint8_t* b = stg + bsel * C::BUF_BYTES;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) s32_load(b + g * S32_BYTES, prow ? prow + g * H : nullptr, lane);
-        s64_load(b + 4 * S32_BYTES, cprow, lane);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      int it = 0, gi = 0;
-      int32_t tokc = tok_of(cta);
-      if (cta < num_tiles) issue_loads(cta, 0, 0, tokc);
+      // ---- forward.  64 hidden units per tile = four column groups of 16; the four warps of a TMEM lane quarter take one
+      // group each.  Per tile and warp: inputs (x-projection rows gathered from the fp16 table, previous cell) -> staging by
+      // cp.async (issued before the accumulator is awaited), TMEM + staging -> gates / c / h in place, out by TMA.
+      const int grp = (warp - 2) >> 2;
+      float* sBias = reinterpret_cast<float*>(stg_all + C::EW * C::STG_PER_WARP);
+      for (int i = (int)threadIdx.x - 64; i < 4 * H; i += 32 * C::EW) sBias[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * C::EW) : "memory");          // epilogue warps only
+      uint8_t* sG = stg; uint8_t* sC = stg + 4 * S32_BYTES; uint8_t* sH = sC + S64_BYTES;
+      int it = 0;
       for (int tile = cta; tile < num_tiles; tile += ncta, ++it) {
         const int buf = it & 1;
         const uint32_t bph = (it >> 1) & 1;
-        const int next_tile = tile + ncta;
-        const int32_t tokn = tok_of(next_tile);                   // used one group later: its latency is hidden
         const int m0 = (tile / num_n) * 2 * BM16 + (int)rank * BM16;
         const int nt = tile % num_n;
         const int64_t row = (int64_t)m0 + q * 32 + lane;
         const bool row_ok = row < p.R;
         const float keep = (row_ok && p.mask_ids && p.mask_ids[row] == 0) ? 0.f : 1.f;
         const int r0 = m0 + q * 32;
-        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int grp = 0; grp < 2; ++grp, ++gi) {
-          const int bsel = gi & 1;
-          uint8_t* sG = stg + bsel * C::BUF_BYTES; uint8_t* sC = sG + 4 * S32_BYTES; uint8_t* sH = sC + S64_BYTES;
-          const int j = nt * 64 + half * 32 + grp * 16;          // first hidden unit of the group
-          const int tc0 = half * 32 + grp * 16;                  // its column inside a gate block of the accumulator
-          const bool have_next = grp == 0 || next_tile < num_tiles;
-          if (have_next) {
-            if (lane == 0) bulk_wait_read0();                    // the other buffer's TMA stores (previous group) have read it
-            __syncwarp();
-            if (grp == 0) issue_loads(tile, 1, bsel ^ 1, tokc); else issue_loads(next_tile, 0, bsel ^ 1, tokn);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this group's inputs have landed
-          } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-          }
-          __syncwarp();
-          if (grp == 0) { mbar_wait(&tfull[buf], bph); tc_fence_after(); }
-          float acc[2][4][8];
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-            for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * 64 + tc0 + sub * 8, acc[sub][g]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            float cp[8], cn[8], hn[8];
-            s64_get8(sC, lane, sub, cp);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float x[8];
-              unpack8(*s32_at(sG + g * S32_BYTES, lane, sub), x);
-              const float4 b0 = *reinterpret_cast<const float4*>(sBias + g * H + j + sub * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(sBias + g * H + j + sub * 8 + 4);
-              float* a = acc[sub][g];
-              a[0] += x[0] + b0.x; a[1] += x[1] + b0.y; a[2] += x[2] + b0.z; a[3] += x[3] + b0.w;
-              a[4] += x[4] + b1.x; a[5] += x[5] + b1.y; a[6] += x[6] + b1.z; a[7] += x[7] + b1.w;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float gi_ = fsigmoid(acc[sub][0][e]), gf = fsigmoid(acc[sub][1][e]), go = fsigmoid(acc[sub][2][e]),
-                          gg = ftanh(acc[sub][3][e]);
-              const float c_ = gf * cp[e] + gi_ * gg;
-              acc[sub][0][e] = gi_ * keep; acc[sub][1][e] = gf * keep; acc[sub][2][e] = go * keep; acc[sub][3][e] = gg * keep;
-              cn[e] = c_ * keep; hn[e] = go * ftanh(c_) * keep;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *s32_at(sG + g * S32_BYTES, lane, sub) = pack8(acc[sub][g]);
-            s64_put8(sC, lane, sub, cn);
-            *s32_at(sH, lane, sub) = pack8(hn);
-            if (p.h32_out && row_ok) {                  // last step only: the fp32 h that meets the encoder output
-              float4* o = reinterpret_cast<float4*>(p.h32_out + row * H + j + sub * 8);
-              o[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-              o[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.save_gates) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) tma_store_2d(&em.g16, sG + g * S32_BYTES, g * H + j, r0);
-            }
-            tma_store_2d(&em.c, sC, j, r0);
-            tma_store_2d(&em.h16, sH, j, r0);
-            bulk_commit();
-          }
-          __syncwarp();
-        }
-        tokc = tokn;
-        tc_fence_before();
+        const int j = nt * 64 + grp * 16;                      // first hidden unit of this warp's group
+        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + grp * 16;
+        const __half* prow = row_ok ? p.ptable + (int64_t)__ldg(p.tok + row) * 4 * H + j : nullptr;
+        const float* cprow = (row_ok && p.c_prev) ? p.c_prev + row * H + j : nullptr;
+        if (lane == 0) bulk_wait_read0();                      // the previous tile's TMA stores have read the staging tiles
         __syncwarp();
-        if (lane == 0) {                                // the accumulator buffer may be overwritten by the leader's MMAs
+#pragma unroll
+        for (int g = 0; g < 4; ++g) s32_load(sG + g * S32_BYTES, prow ? prow + g * H : nullptr, lane);
+        s64_load(sC, cprow, lane);
+        mbar_wait(&tfull[buf], bph);                           // the loads fly while the MMAs of this tile finish
+        tc_fence_after();
+        cp_wait_all();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          float a[4][8], cp[8], hn[8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * 64 + sub * 8, a[g]);
+          tmem_ld_wait();
+          s64_get8(sC, lane, sub, cp);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float x[8];
+            unpack8(*s32_at(sG + g * S32_BYTES, lane, sub), x);
+            const float4 b0 = *reinterpret_cast<const float4*>(sBias + g * H + j + sub * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sBias + g * H + j + sub * 8 + 4);
+            a[g][0] += x[0] + b0.x; a[g][1] += x[1] + b0.y; a[g][2] += x[2] + b0.z; a[g][3] += x[3] + b0.w;
+            a[g][4] += x[4] + b1.x; a[g][5] += x[5] + b1.y; a[g][6] += x[6] + b1.z; a[g][7] += x[7] + b1.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float gi = sig16(a[0][e]), gf = sig16(a[1][e]), go = sig16(a[2][e]), gg = tanh16(a[3][e]);
+            const float c_ = (gf * cp[e] + gi * gg) * keep;
+            a[0][e] = gi * keep; a[1][e] = gf * keep; a[2][e] = go * keep; a[3][e] = gg * keep;
+            cp[e] = c_; hn[e] = go * tanh16(c_) * keep;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *s32_at(sG + g * S32_BYTES, lane, sub) = pack8(a[g]);
+          s64_put8(sC, lane, sub, cp);
+          *s32_at(sH, lane, sub) = pack8(hn);
+          if (p.h32_out && row_ok) {                  // last step only: the fp32 h that meets the encoder output
+            float4* o = reinterpret_cast<float4*>(p.h32_out + row * H + j + sub * 8);
+            o[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            o[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+          }
+        }
+        tc_fence_before();                            // the accumulator has been read: hand it back before the stores leave
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
           if (!leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
           else mbar_arrive(&tempty[buf]);
+          if (p.save_gates) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tma_store_2d(&em.g16, sG + g * S32_BYTES, g * H + j, r0);
+          }
+          tma_store_2d(&em.c, sC, j, r0);
+          tma_store_2d(&em.h16, sH, j, r0);
+          bulk_commit();
         }
+        __syncwarp();
       }
     } else {
     int it = 0;
@@ -761,7 +734,7 @@ static void launch16(LaunchCtx& cx, const CUtensorMap& tA, const CUtensorMap& tB
   if (num_tiles > pmax) { const int rounds = cdiv(num_tiles, pmax); pairs = cdiv(num_tiles, rounds); }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(THREADS16);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::TOTAL;
   cfg.stream = cx.stream;
   cudaLaunchAttribute at[1];
