@@ -27,9 +27,10 @@ namespace tc {
 constexpr int BM16 = 128;        // rows per CTA (UMMA M = 256 per pair)
 constexpr int BK16 = 64;         // halves per k-block = one 128-byte swizzle row
 constexpr int UK16 = 16;         // kind::f16: 32 bytes per instruction
-// epilogue warps: 16 forward (four per TMEM lane quarter, one 16-unit column group each: the pointwise half is
-// instruction-issue / latency bound, and four warps per scheduler hide what two could not), 8 backward (HBM-bound)
-template <int MODE> struct EW16T { static constexpr int N = MODE == 0 ? 16 : 8; };
+// epilogue warps: 16 = four per TMEM lane quarter, each with its own share of the tile's columns.  The pointwise halves are
+// latency-bound per warp (gather / saved-activation loads, MUFU chains): four warps per scheduler hide what two could not
+// (forward step 176 -> 109 us, with the pad-token gather skip; backward: 8 sequential groups per warp -> 4)
+template <int MODE> struct EW16T { static constexpr int N = 16; };
 constexpr int STAGE16 = 32768;   // 16 KB of A (this CTA's 128 rows) + 16 KB of B (this CTA's half of the 256-column tile)
 
 // instruction descriptor, kind::f16: D = f32 (c_format 1), A = B = f16 (format 0)
@@ -352,8 +353,9 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int r0 = m0 + q * 32;
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       {
-        // ---- backward: 256 hidden units per tile, this warp takes 128 of them in eight groups of 16
-        const int j0 = nt * 256 + half * 128;
+        // ---- backward: 256 hidden units per tile, the warp's column slice = 256 / (EW/4) of them, in groups of 16
+        constexpr int NSL = C::EW / 4, GPW = 256 / NSL / 16;      // column slices per tile, groups per warp
+        const int j0 = nt * 256 + half * (256 / NSL);
         const __half* grow = row_ok ? p.gsave + row * 4 * H : nullptr;
         const float* cprow = (row_ok && p.c_prev) ? p.c_prev + row * H : nullptr;
         const float* ccrow = row_ok ? p.c_cur + row * H : nullptr;
@@ -361,9 +363,9 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         uint8_t* sG = stg; uint8_t* sCP = stg + 4 * S32_BYTES; uint8_t* sCC = sCP + S64_BYTES; uint8_t* sDC = sCC + S64_BYTES;
         bool waited = false;
 #pragma unroll 1
-        for (int grp = 0; grp < 8; ++grp) {
+        for (int grp = 0; grp < GPW; ++grp) {
           const int j = j0 + grp * 16;
-          const int tc0 = half * 128 + grp * 16;
+          const int tc0 = half * (256 / NSL) + grp * 16;
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
 #pragma unroll
@@ -373,7 +375,7 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           s64_load(sDC, dcrow ? dcrow + j : nullptr, lane);
           if (!waited) { mbar_wait(&tfull[buf], bph); tc_fence_after(); waited = true; }
           cp_wait_all();
-#pragma unroll
+#pragma unroll 1
           for (int sub = 0; sub < 2; ++sub) {
             float dh[8], g[4][8], cp[8], cc[8], dc[8], out[4][8], dcn[8];
             tmem_ld8(taddr + tc0 + sub * 8, dh);
@@ -386,7 +388,7 @@ k_lstm16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
-              const float tcv = ftanh(cc[e]);
+              const float tcv = tanh16(cc[e]);
               const float d = (dc[e] + dh[e] * go * (1.f - tcv * tcv)) * keep;
               const float dhe = dh[e] * keep;
               out[0][e] = d * gg_ * gi * (1.f - gi);
@@ -613,7 +615,7 @@ k_lstm16_bwd_last(const __half* __restrict__ gates, const float* __restrict__ c_
   for (int e = 0; e < 8; ++e) {
     const float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
     const float dhe = dh[e] * s * keep;
-    const float tcv = ftanh(cc[e]);
+    const float tcv = tanh16(cc[e]);
     const float d = dhe * go * (1.f - tcv * tcv);
     out[0][e] = d * gg_ * gi * (1.f - gi);
     out[1][e] = d * cp[e] * gf * (1.f - gf);
