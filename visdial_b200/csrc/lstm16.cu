@@ -29,8 +29,9 @@ constexpr int BK16 = 64;         // halves per k-block = one 128-byte swizzle ro
 constexpr int UK16 = 16;         // kind::f16: 32 bytes per instruction
 // epilogue warps: 16 = four per TMEM lane quarter, each with its own share of the tile's columns.  The pointwise halves are
 // latency-bound per warp (gather / saved-activation loads, MUFU chains): four warps per scheduler hide what two could not
-// (forward step 176 -> 109 us, with the pad-token gather skip; backward: 8 sequential groups per warp -> 4)
-template <int MODE> struct EW16T { static constexpr int N = 16; };
+// (forward step 176 -> 109 us, with the pad-token gather skip).  The backward step stays at 8: its 16-warp variant needs 160 KB
+// of staging, which leaves two 32 KB pipeline stages for a K = 2048 main loop — measured 209 us against 138 us with 8 warps / 4 stages
+template <int MODE> struct EW16T { static constexpr int N = MODE == 0 ? 16 : 8; };
 constexpr int STAGE16 = 32768;   // 16 KB of A (this CTA's 128 rows) + 16 KB of B (this CTA's half of the 256-column tile)
 
 // instruction descriptor, kind::f16: D = f32 (c_format 1), A = B = f16 (format 0)
