@@ -216,13 +216,7 @@ def test_model_retrieve_over_the_device_dataloader(enc, dec):
     d2.close(); model.engine.close()
 
 
-_UNRUN = "comparison made tie-robust after the last GPU minutes of round 1 were spent (lf-ques ran green; hrea reached the " \
-         "comparison and differed only in which zero-score token a stale beam column picked); run with VD_RUN_UNVERIFIED=1"
-_unrun = pytest.mark.skipif(__import__("os").environ.get("VD_RUN_UNVERIFIED") != "1", reason=_UNRUN)
-
-
-@pytest.mark.parametrize("enc", ["lf-ques", pytest.param("hrea-ques-im-hist", marks=_unrun),
-                                 pytest.param("mn-att-ques-im-hist", marks=_unrun)])
+@pytest.mark.parametrize("enc", ["lf-ques", "hrea-ques-im-hist", "mn-att-ques-im-hist", "lf-ques-im-hist"])
 def test_generate_answers_matches_oracle(enc):
     """Model:generateAnswers (model.lua:432-613) — beam search and sampling driven through vd_gen_decoder_step on
     batches the device dataloader assembles — against oracle.generate_answers on the same dialog (fp32 math mode)."""

@@ -113,6 +113,7 @@ def test_train_iteration_adam_matches_oracle(enc, dec):
     state = {}
     lr = p["learningRate"]
     for it in range(1, 4):
+        lr_used = m.optims["learningRate"]
         m.trainIteration(DL())
         psite = {O.SITE_FUSION: p["dropout"]}
         ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(1234, it, psite)), p,
@@ -125,6 +126,25 @@ def test_train_iteration_adam_matches_oracle(enc, dec):
         got[:p["embedSize"]] = 0
         # Adam normalises the step to ~lr: compare in units of lr
         assert float(np.abs(got - W.numpy()).max()) < 0.05 * p["learningRate"], it
+        # The optimiser formula itself, isolated from gradient noise: replay optim_updates.lua:62-91 in fp64 on the gradient
+        # the engine consumed (get_gradients after the step = clamped dW) and compare m, v, t and the weights directly —
+        # an eps-placement or bias-correction slip moves small-gradient weights by O(lr), far outside these bounds.
+        g = m.engine.get_gradients().astype(np.float64)
+        if it == 1:
+            m_ref, v_ref, w_ref = np.zeros_like(g), np.zeros_like(g), flat0.astype(np.float64)
+        w_ref[:p["embedSize"]] = 0                  # LookupTableMaskZero re-zeroes the pad row at every forward
+        m_ref = 0.9 * m_ref + 0.1 * g
+        v_ref = 0.999 * v_ref + 0.001 * g * g
+        step = lr_used * np.sqrt(1 - 0.999 ** it) / (1 - 0.9 ** it)
+        w_ref = w_ref - step * m_ref / (np.sqrt(v_ref) + 1e-8)
+        em, ev, et = m.engine.optim_state()
+        assert et == it
+        assert float(np.abs(em - m_ref).max()) <= 1e-6 * float(np.abs(m_ref).max()) + 1e-12, it
+        assert float(np.abs(ev - v_ref).max()) <= 1e-6 * float(np.abs(v_ref).max()) + 1e-20, it
+        raw = m.engine.get_parameters().astype(np.float64)
+        raw[:p["embedSize"]] = 0
+        w_chk = w_ref.copy(); w_chk[:p["embedSize"]] = 0
+        assert float(np.abs(raw - w_chk).max()) < 2e-3 * lr_used + 3e-7, (it, float(np.abs(raw - w_chk).max()))
     assert m.optims["learningRate"] == pytest.approx(lr)
     m.engine.close()
 
