@@ -116,6 +116,12 @@ int vd_set_dropout_seed(vd_engine* e, uint64_t seed, uint64_t iteration);
 #define VD_MATH_F16 2         /* TF32 mode + the many-row option LSTM (disc.lua:4-20) with fp16 operands and fp16 saved state
                                  (h, gates, da, x-projection table), fp32 accumulation, fp32 cell state and gradients */
 int vd_set_math_mode(vd_engine* e, int32_t mode);
+/* gen decoder: on = 1 lets vd_decoder_forward keep the (rows, vocabSize) log-probabilities on chip when the caller only
+ * passes decOut on to the criterion (decoder:forward -> criterion:forward, model.lua:313-314): decOut_dev is then NULL, the
+ * projection's epilogue keeps the softmax statistics and the target log-probability, and vd_criterion_backward recomputes the
+ * projection with the softmax gradient fused in.  Default 0: decOut is materialised (LogSoftMax output, gen.lua:23-24).
+ * vd_forward_backward and vd_retrieve never hand decOut out and always take the fused route in the tensor-core modes. */
+int vd_set_lazy_decout(vd_engine* e, int32_t on);
 /* Scheduling knob (results are identical either way).  on = 1 (default): the disc decoder's option LSTM (disc.lua:4-20),
  * which does not depend on the encoder until the final dot product, runs on its own stream concurrently with the
  * encoder's forward and backward, its persistent kernels leaving `reserve_sms` SMs (default 16, < 0 keeps the current

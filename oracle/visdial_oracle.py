@@ -577,7 +577,11 @@ def generate_answers(ctx: Ctx, cfg, P, batch, start_token: int, end_token: int, 
                     explore = 1 if step == 1 else beam_size                                  # :516
                     logp, nH, nC = decoder_gen_step(cfg, P, beams[step - 1], H, Cc)          # :519-526
                     for w in range(explore):                                                 # :529
-                        top_p, top_i = torch.topk(logp[w], beam_size, largest=True, sorted=True)   # :538-542
+                        # :538-542 torch.topk(beamSize): sorted descending; ties (an all-zero MaskZero'd row, duplicate
+                        # beams) are resolved 'lower class index first' — TH's order among ties is unspecified, the rule is
+                        # pinned here and in visdial_b200/model.py so that both walk the same hypotheses
+                        top_i = torch.argsort(-logp[w], stable=True)[:beam_size]
+                        top_p = logp[w][top_i]
                         for cnd in range(beam_size):                                         # :544
                             cb = beams[:, w].clone()
                             tok = int(top_i[cnd]) + 1                                        # class index -> 1-based token id

@@ -336,3 +336,62 @@ def test_f16_option_lstm_matches_oracle(B, T0):
         s = seg_slices(p)[name]
         r = ref["grads"][name].numpy().ravel()
         assert _rel(res[VD_MATH_F16][1][s], r) < 2.0 * _rel(res[VD_MATH_TF32][1][s], r) + 1e-3, name
+
+
+@pytest.mark.parametrize("enc", ["lf-ques", "hrea-ques-im-hist"])
+def test_fused_vocab_softmax_matches_oracle_and_unfused(enc):
+    """gen decoder, tensor-core mode: vd_forward_backward keeps the (rows, V) logits on chip (projection epilogue = online
+    softmax statistics + target logit; backward = projection recomputed with softmax - onehot in the epilogue).  Same loss and
+    gradients as the oracle (TF32 tolerance) and as the materialising module-level path of the same mode (1e-4: both TF32)."""
+    p = small_params(enc, "gen", rnnHiddenSize=128, embedSize=64, vocabSize=300, imgFeatureSize=256, imgEmbedSize=32)
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 13, seed=7, max_ques_len=9, max_ans_len=6, max_cap_len=12, max_hist_len=14, empty_round_every=4)
+    ref = O.forward_backward(O.Ctx(train=True, mask_fn=philox.make_mask_fn(11, 3), structure="batched"), p, torch_params(p, flat),
+                             torch_batch(nb))
+    out = {}
+    for fused in (True, False):
+        eng = Engine(p)
+        eng.set_math_mode(VD_MATH_TF32)
+        eng.set_parameters(flat)
+        eng.set_training(1)
+        eng.set_dropout_seed(11, 3)
+        eng.zero_grad()
+        b = Batch(nb)
+        if fused:
+            loss = eng.forward_backward(b)                       # one crossing: decOut is never handed out
+        else:                                                    # module-level calls: decOut materialised (LogSoftMax output)
+            eng.encoder_forward(b); eng.forward_connect(); eng.decoder_forward(b)
+            loss = eng.criterion_forward(b)
+            eng.criterion_backward(b); eng.decoder_backward(b)
+            eng.encoder_backward(b, eng.backward_connect(b))
+        out[fused] = (loss, eng.get_gradients())
+        eng.close()
+    lf, gf = out[True]
+    lu, gu = out[False]
+    assert abs(lf - ref["loss"]) < 5e-3 * abs(ref["loss"]), (lf, ref["loss"])
+    assert abs(lf - lu) < 2e-4 * abs(lu), (lf, lu)
+    for name, s in seg_slices(p).items():
+        r = ref["grads"][name].numpy().ravel()
+        if np.abs(r).max() < 1e-7:
+            continue
+        assert _rel(gf[s], r) < 3e-2, name
+        assert _rel(gf[s], gu[s]) < 2e-3, name
+
+
+def test_fused_vocab_gen_retrieval_ranks():
+    """gen retrieval (model.lua:392-420, utils.computeLhood): the option likelihoods come from the fused projection epilogue in the
+    tensor-core mode; ranks agree with the oracle wherever its likelihood gaps exceed the TF32 noise, and with fp32 mode mostly."""
+    p = small_params("lf-ques", "gen", rnnHiddenSize=128, embedSize=64, vocabSize=300, numOptions=10)
+    flat = init_parameters(p, seed=3)
+    nb = make_batch(p, 7, seed=9, max_ques_len=9, max_ans_len=6, gen_eval=True)
+    ref = O.retrieve_batch(O.Ctx(), p, torch_params(p, flat), torch_batch(nb), use_gt=False).numpy()
+    got = {}
+    for mode in (VD_MATH_TF32, VD_MATH_FP32):
+        eng = Engine(p)
+        eng.set_math_mode(mode)
+        eng.set_parameters(flat)
+        got[mode] = eng.retrieve(Batch(nb), use_gt=False)
+        eng.close()
+    assert np.array_equal(got[VD_MATH_FP32], ref)
+    assert (got[VD_MATH_TF32] == ref).mean() > 0.9
+    assert np.array_equal(np.sort(got[VD_MATH_TF32], 1), np.sort(ref, 1))

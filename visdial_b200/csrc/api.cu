@@ -174,6 +174,7 @@ int vd_decoder_forward(vd_engine* h, const vd_batch* b, const float** decOut) {
     if (decOut) *decOut = e->cfg.dec == vd::DEC_DISC ? e->scores : e->logp;
   })
 }
+int vd_set_lazy_decout(vd_engine* h, int32_t on) { VD_TRY({ ENG(h)->want_logp = on == 0; }) }
 int vd_criterion_forward(vd_engine* h, const vd_batch* b, float* loss) {
   VD_TRY({ (void)b; NOTNULL(loss); *loss = ENG(h)->criterion_forward(); })
 }
@@ -191,7 +192,10 @@ int vd_forward_backward(vd_engine* h, const vd_batch* b, int32_t only_forward, f
     Engine* e = ENG(h);
     e->encoder_forward(b);
     e->forward_connect();
-    e->decoder_forward();
+    const bool saved_want = e->want_logp;
+    e->want_logp = false;                 // whole-step call: decOut is not handed out, the gen logits may stay on chip
+    try { e->decoder_forward(); } catch (...) { e->want_logp = saved_want; throw; }
+    e->want_logp = saved_want;
     float l = e->criterion_forward();
     if (loss) *loss = l;
     if (!only_forward) {

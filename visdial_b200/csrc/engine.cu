@@ -1114,9 +1114,26 @@ void Engine::decoder_forward() {
     dec2 = make_run(db.Ta, N, H, H, seg("dec.lstm2.weight"), dec1.h, nullptr, ids_ai);
     dec2.h0 = gen_h0[1]; dec2.c0 = gen_c0[1];
     lstm_forward(dec2, true);
-    logp = arena.get<float>(N * db.Ta * cfg.V);
-    linear_fwd(seg("dec.out.weight"), dec2.h, N * db.Ta, logp, 0);
-    logsoftmax_rows(cx, logp, ids_ai, N * db.Ta, cfg.V);            // gen.lua:23-24 (MaskZero)
+    fused_vocab_fwd = false;
+    const int64_t rows = N * db.Ta;
+    const int wo = seg("dec.out.weight");
+    if (!want_logp && tcmode() && db.answer_out) {
+      // whole-step entry point: nobody reads decOut, only the criterion does — keep the logits on chip
+      ids_ao = arena.get<int32_t>(rows);
+      transpose_ids(cx, db.answer_out, ids_ao, N, db.Ta);
+      voc_nparts = vocab_lse_nparts(cfg.V);
+      voc_pm = arena.get<float>(rows * voc_nparts); voc_ps = arena.get<float>(rows * voc_nparts);
+      voc_tl = arena.get<float>(rows); voc_lse = arena.get<float>(rows);
+      LaunchCtx::Scope sc(&cx, "vocab_lse", 2.0 * rows * cfg.V * H, 4.0 * (rows * (double)H + (double)cfg.V * H + 2.0 * rows * voc_nparts));
+      fused_vocab_fwd = vocab_lse_tc(cx, (int)rows, cfg.V, H, dec2.h, H, Wp(wo), H, Wp(wo + 1), ids_ao, voc_pm, voc_ps, voc_tl);
+    }
+    if (!fused_vocab_fwd) {
+      logp = arena.get<float>(rows * cfg.V);
+      linear_fwd(wo, dec2.h, rows, logp, 0);
+      logsoftmax_rows(cx, logp, ids_ai, rows, cfg.V);            // gen.lua:23-24 (MaskZero)
+    } else {
+      logp = nullptr;
+    }
   }
 }
 
@@ -1128,11 +1145,15 @@ float Engine::criterion_forward() {
     xent_fwd(cx, scores, db.answer_ind, row_loss, N, cfg.K);
     reduce_sum(cx, row_loss, scalars_dev, N, 1.f / (float)N);        // CrossEntropyCriterion: mean
   } else {
-    VD_REQUIRE(logp && db.answer_out, VD_E_STATE, "criterion: decoder_forward / answer_out missing");
-    ids_ao = arena.get<int32_t>(N * db.Ta);
-    transpose_ids(cx, db.answer_out, ids_ao, N, db.Ta);
+    VD_REQUIRE((logp || fused_vocab_fwd) && db.answer_out, VD_E_STATE, "criterion: decoder_forward / answer_out missing");
     row_loss = arena.get<float>(N * db.Ta);
-    nll_fwd(cx, logp, ids_ao, ids_ai, row_loss, N * db.Ta, cfg.V);
+    if (fused_vocab_fwd) {
+      vocab_lse_finish(cx, voc_pm, voc_ps, voc_nparts, voc_tl, ids_ao, ids_ai, voc_lse, row_loss, -1.f, 0, N * db.Ta);
+    } else {
+      ids_ao = arena.get<int32_t>(N * db.Ta);
+      transpose_ids(cx, db.answer_out, ids_ao, N, db.Ta);
+      nll_fwd(cx, logp, ids_ao, ids_ai, row_loss, N * db.Ta, cfg.V);
+    }
     reduce_sum(cx, row_loss, scalars_dev, N * db.Ta, 1.f);            // ClassNLL sizeAverage=false
   }
   float loss = 0.f;
@@ -1148,9 +1169,17 @@ void Engine::criterion_backward() {
     dscores = arena.get<float>(N * cfg.K);
     xent_bwd(cx, scores, db.answer_ind, dscores, N, cfg.K);
   } else {
-    VD_REQUIRE(logp && ids_ao, VD_E_STATE, "criterion_backward before criterion_forward");
+    VD_REQUIRE((logp || fused_vocab_fwd) && ids_ao, VD_E_STATE, "criterion_backward before criterion_forward");
     dlogits = arena.get<float>(N * db.Ta * cfg.V);
-    nll_bwd(cx, logp, ids_ao, ids_ai, dlogits, N * db.Ta, cfg.V);
+    if (fused_vocab_fwd) {
+      const int wo = seg("dec.out.weight");
+      LaunchCtx::Scope sc(&cx, "vocab_dlogits", 2.0 * N * db.Ta * cfg.V * cfg.H, 4.0 * N * db.Ta * (double)cfg.V);
+      bool ok = vocab_dlogits_tc(cx, (int)(N * db.Ta), cfg.V, cfg.H, dec2.h, cfg.H, Wp(wo), cfg.H, Wp(wo + 1), ids_ao, ids_ai, voc_lse,
+                                 dlogits, cfg.V);
+      VD_REQUIRE(ok, VD_E_STATE, "vocab_dlogits_tc refused a shape vocab_lse_tc took");
+    } else {
+      nll_bwd(cx, logp, ids_ao, ids_ai, dlogits, N * db.Ta, cfg.V);
+    }
   }
 }
 
@@ -1263,11 +1292,27 @@ void Engine::gen_option_lhood() {
   lstm_forward(l2, true);
   lhood = arena.get<float>(Ro);
   VD_CUDA_CHECK(cudaMemsetAsync(lhood, 0, (size_t)Ro * sizeof(float), cx.stream));
-  float* logits = arena.get<float>(Ro * V);
   int wo = seg("dec.out.weight");
+  // utils.computeLhood per time step.  Tensor-core modes: the vocabulary projection keeps its (N*100, V) logits on chip and
+  // writes (max, sum exp) partials + the target logit only (20 MB per step instead of 1.28 GB written and read back)
+  const int nparts = vocab_lse_nparts(V);
+  float *pm = nullptr, *ps = nullptr, *tl = nullptr, *logits = nullptr;
+  bool fused = tcmode() && Ro >= 64 && V >= 256;
+  if (fused) { pm = arena.get<float>(Ro * nparts); ps = arena.get<float>(Ro * nparts); tl = arena.get<float>(Ro); }
   for (int t = 0; t < db.To; ++t) {
-    linear_fwd(wo, l2.h + (int64_t)t * Ro * H, Ro, logits, 0);
-    lhood_accumulate(cx, logits, oo + (int64_t)t * Ro, oi + (int64_t)t * Ro, lhood, Ro, V);
+    const float* ht = l2.h + (int64_t)t * Ro * H;
+    if (fused) {
+      LaunchCtx::Scope sc(&cx, "vocab_lse", 2.0 * Ro * V * H, 4.0 * (Ro * (double)H + (double)V * H + 2.0 * Ro * nparts));
+      fused = vocab_lse_tc(cx, (int)Ro, V, H, ht, H, Wp(wo), H, Wp(wo + 1), oo + (int64_t)t * Ro, pm, ps, tl);
+      VD_REQUIRE(fused || t == 0, VD_E_STATE, "vocab_lse_tc changed its mind between time steps");
+    }
+    if (fused) {
+      vocab_lse_finish(cx, pm, ps, nparts, tl, oo + (int64_t)t * Ro, oi + (int64_t)t * Ro, nullptr, lhood, 1.f, 1, Ro);
+    } else {
+      if (!logits) logits = arena.get<float>(Ro * V);
+      linear_fwd(wo, ht, Ro, logits, 0);
+      lhood_accumulate(cx, logits, oo + (int64_t)t * Ro, oi + (int64_t)t * Ro, lhood, Ro, V);
+    }
   }
 }
 

@@ -148,6 +148,13 @@ struct Engine {
   const float *gen_h0[2] = {nullptr, nullptr}, *gen_c0[2] = {nullptr, nullptr};
   float *gen_dh0[2] = {nullptr, nullptr}, *gen_dc0[2] = {nullptr, nullptr};
   float *dEncFromDec = nullptr;
+  // gen decoder, fused vocabulary softmax (tensor-core modes, whole-step entry points): the (rows, V) log-probabilities are
+  // never materialised — the projection's epilogue keeps per-slice (max, sum exp) and the target logit, the criterion reads
+  // those, the backward recomputes the projection with the softmax gradient in its epilogue.  want_logp = a caller (the
+  // module-level vd_decoder_forward) asked for decOut itself.
+  bool want_logp = true, fused_vocab_fwd = false;
+  float *voc_pm = nullptr, *voc_ps = nullptr, *voc_tl = nullptr, *voc_lse = nullptr;
+  int voc_nparts = 0;
   // connect grads handed to the encoder LSTMs (gen.lua:45-60)
   const float *conn_dh_l1 = nullptr, *conn_dc_l1 = nullptr, *conn_dc_l2 = nullptr;
 

@@ -22,7 +22,11 @@ constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
 constexpr int EPI_WARPS = 8;     // 2 warps per TMEM lane quarter, each takes half of the tile's columns
 // threads per CTA = 64 (TMA producer warp + MMA issuer warp) + 32 * epilogue warps (template parameter EW)
 
-enum { MODE_GENERIC = 0, MODE_LSTM_FWD = 1, MODE_LSTM_BWD = 2 };
+enum { MODE_GENERIC = 0, MODE_LSTM_FWD = 1, MODE_LSTM_BWD = 2, MODE_LSE = 3, MODE_DLOGIT = 4 };
+// MODE_LSE    : vocabulary projection whose (rows, V) logits never leave the chip: per row and column slice only the running
+//               max, the sum of exponentials and the target's logit are written (gen.lua:23-24 + the criterion of model.lua:33-36
+//               / utils.computeLhood, utils.lua:86-102)
+// MODE_DLOGIT : the same contraction recomputed in the backward pass with the epilogue  C = keep * (exp(x - lse[row]) - onehot)
 
 struct Params {
   int M, N, K;                    // GEMM sizes (N = output columns; LSTM_FWD: N = 4H, LSTM_BWD: N = H)
@@ -36,6 +40,9 @@ struct Params {
   const float* c_prev; float* c_out; float* h_out; const int32_t* mask_ids;
   // lstm bwd
   const float* gsave; const float* c_cur; const float* dh_ext; float* dc_carry; float* da;
+  // fused vocabulary softmax (MODE_LSE / MODE_DLOGIT): 1-based target class per row (0 = none), maskzero ids per row
+  const int32_t* tgt; const int32_t* row_ids; const float* lse;
+  float* part_max; float* part_sum; float* tgt_logit; int nparts;      // (M, nparts) partials, nparts = column tiles * slices
 };
 
 __device__ __forceinline__ void ld8(const float* p, float* d) {
@@ -62,8 +69,8 @@ __device__ __forceinline__ void st8_cs(float* p, const float* v) {
 // 16-byte piece of 32 different lines per instruction, which is what saturated L1TEX before).
 constexpr int STG_ARR_BYTES = 32 * 16 * 4;
 template <int BN, int MODE, int CG, int EW = EPI_WARPS> struct StageCfg {
-  static constexpr bool ON = MODE == MODE_GENERIC || (CG == 2 && (BN == 256 || (BN == 128 && MODE == MODE_LSTM_BWD)));
-  static constexpr int ARR = !ON ? 0 : (MODE == MODE_GENERIC ? 1 : MODE == MODE_LSTM_FWD ? 6 : 7);
+  static constexpr bool ON = MODE == MODE_GENERIC || MODE == MODE_DLOGIT || (CG == 2 && (BN == 256 || (BN == 128 && MODE == MODE_LSTM_BWD)));
+  static constexpr int ARR = !ON ? 0 : ((MODE == MODE_GENERIC || MODE == MODE_DLOGIT) ? 1 : MODE == MODE_LSTM_FWD ? 6 : 7);
   static constexpr int BYTES = EW * ARR * STG_ARR_BYTES;
 };
 template <int BN, int CG = 1, int STG_BYTES = 0, int MAXST = 16> struct SmemLayout {
@@ -261,7 +268,41 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 
-      if (MODE == MODE_GENERIC) {
+      if (MODE == MODE_LSE) {
+        // online softmax statistics of this warp's column slice of the tile: nothing but (max, sum exp, target logit) leaves
+        const int n0 = nt * BN;
+        const int tcol = row_ok ? p.tgt[row] - 1 : -1;
+        float mrun = -INFINITY, srun = 0.f, tl = 0.f;
+        bool has = false;
+#pragma unroll 1
+        for (int c = half * (BN / NH); c < (half + 1) * (BN / NH); c += 8) {
+          if (n0 + c >= p.N) break;                 // warp-uniform
+          float v[8];
+          tmem_ld8(taddr + c, v);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + c + j;
+            const bool ok = n < p.N;
+            const float x = ok ? v[j] + (p.bias ? __ldg(p.bias + n) : 0.f) : -INFINITY;
+            v[j] = x;
+            if (ok && n == tcol) { tl = x; has = true; }
+            mx = fmaxf(mx, x);
+          }
+          const float mnew = fmaxf(mrun, mx);
+          float add = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) add += __expf(v[j] - mnew);      // exp(-inf) = 0 for the clipped columns
+          srun = srun * __expf(mrun - mnew) + add;
+          mrun = mnew;
+        }
+        if (row_ok) {
+          const int64_t pi = row * p.nparts + nt * NH + half;
+          p.part_max[pi] = mrun; p.part_sum[pi] = srun;
+          if (has) p.tgt_logit[row] = tl;
+        }
+      } else if (MODE == MODE_GENERIC || MODE == MODE_DLOGIT) {
         // 16 output columns at a time through the warp's staging array; C leaves (and, for beta != 0, enters)
         // as 64-byte-swizzled boxes: TMA tensor store / cp.async load.  Rows >= M and columns >= N are clipped.
         const int n0 = nt * BN;
@@ -291,6 +332,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tmem_ld8(taddr + c + sub * 8, v);
             tmem_ld_wait();
             if (p.beta != 0.f) stg_get8(stg, 0, lane, sub, old);
+            if (MODE == MODE_DLOGIT) {
+              // d loss / d logit of the sum criterion: softmax - onehot on kept rows (input token != pad, target != pad)
+              const int tg = row_ok ? p.tgt[row] : 0;
+              const bool keepr = row_ok && tg > 0 && p.row_ids[row] != 0;
+              const float l = keepr ? p.lse[row] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int n = n0 + c + sub * 8 + j;
+                const float x = v[j] + ((p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f);
+                v[j] = keepr ? __expf(x - l) - (n == tg - 1 ? 1.f : 0.f) : 0.f;
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int n = n0 + c + sub * 8 + j;
@@ -298,6 +351,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (p.bias && n < p.N) x += __ldg(p.bias + n);
               if (p.beta != 0.f) x += p.beta * old[j];
               v[j] = p.act == 1 ? ftanh(x) : x;
+            }
             }
             stg_put8(stg, 0, lane, sub, v);
           }
@@ -819,6 +873,36 @@ bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t
   dim3 grid(tiles, (unsigned)splits);
   k_tc_atb<<<grid, ATB_THREADS, AtbSmem::TOTAL, cx.stream>>>(tA, tB, p);
   check_launch(cx, "k_tc_atb");
+  return true;
+}
+
+// Vocabulary projection with the softmax statistics fused into the epilogue (no (rows, V) tensor in HBM):
+//   part_max / part_sum (M, nparts): per column slice running max and sum of exp(x - max);  tgt_logit[m] = x[m, tgt[m]-1]
+int vocab_lse_nparts(int N) { return cdiv(N, 256) * (tc::EPI_WARPS / 4); }
+bool vocab_lse_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                  const int32_t* tgt, float* part_max, float* part_sum, float* tgt_logit) {
+  using namespace tc;
+  if (M < 64 || N < 256 || K < 32) return false;
+  if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
+  Params p = {};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.tgt = tgt; p.part_max = part_max; p.part_sum = part_sum; p.tgt_logit = tgt_logit;
+  p.nparts = vocab_lse_nparts(N);
+  CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 256);
+  launch<256, MODE_LSE>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 256));
+  return true;
+}
+// C[m,n] = keep[m] * (exp(A B^T + bias - lse[m]) - [n == tgt[m]-1])   (backward of log-softmax + ClassNLL, recomputed)
+bool vocab_dlogits_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                      const int32_t* tgt, const int32_t* row_ids, const float* lse, float* C, int64_t ldc) {
+  using namespace tc;
+  if (M < 64 || N < 256 || K < 32) return false;
+  if (!tma_ok(A, lda) || !tma_ok(B, ldb) || !tma_ok(C, ldc)) return false;
+  Params p = {};
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.tgt = tgt; p.row_ids = row_ids; p.lse = lse;
+  EpiMaps em = {};
+  em.g4 = make_tmap(C, M, N, ldc, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap tA = make_tmap(A, M, K, lda, BM), tB = make_tmap(B, N, K, ldb, 256);
+  launch<256, MODE_DLOGIT>(cx, tA, tB, p, cdiv(M, BM) * cdiv(N, 256), &em);
   return true;
 }
 

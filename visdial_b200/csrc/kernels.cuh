@@ -21,6 +21,16 @@ bool gemm_tn_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda,
 bool gemm_atb_tc(LaunchCtx& cx, int M, int N, int64_t K, const float* A, int64_t lda, const int32_t* a_gather,
                  const float* B, int64_t ldb, float* C, int64_t ldc);
 
+// fused vocabulary softmax (gemm_tc.cu, pointwise.cu): the (rows, V) logits of decoders/gen.lua:21-24 never reach HBM
+int vocab_lse_nparts(int N);
+bool vocab_lse_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                  const int32_t* tgt, float* part_max, float* part_sum, float* tgt_logit);
+bool vocab_dlogits_tc(LaunchCtx& cx, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                      const int32_t* tgt, const int32_t* row_ids, const float* lse, float* C, int64_t ldc);
+// lse[r] from the partials; then  out[r] (+)= keep ? sign * (tgt_logit[r] - lse[r]) : 0   (keep: row id != 0 and target > 0)
+void vocab_lse_finish(LaunchCtx& cx, const float* part_max, const float* part_sum, int nparts, const float* tgt_logit,
+                      const int32_t* tgt, const int32_t* row_ids, float* lse, float* out, float sign, int accumulate, int64_t rows);
+
 // ---- ids / embedding ---------------------------------------------------------------------------
 // (rows,T) batch-major -> (T,rows) time-major: the `view(-1,T):t()` of model.lua:256,276,308.
 void transpose_ids(LaunchCtx& cx, const int32_t* src, int32_t* dst, int64_t rows, int T);

@@ -207,6 +207,26 @@ __global__ void k_lstm_pw_bwd(const float* __restrict__ gates, const float* __re
   dc_carry[idx] = dc * gf;
 }
 
+// row log-sum-exp from the per-slice partials of the fused vocabulary projection, then the criterion / likelihood term
+__global__ void k_vocab_lse_finish(const float* __restrict__ pm, const float* __restrict__ ps, int nparts,
+                                   const float* __restrict__ tl, const int32_t* __restrict__ tgt, const int32_t* __restrict__ ids,
+                                   float* __restrict__ lse, float* __restrict__ out, float sign, int accumulate, int64_t rows) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* m = pm + r * nparts; const float* s = ps + r * nparts;
+  float mx = -INFINITY;
+  for (int i = 0; i < nparts; ++i) mx = fmaxf(mx, m[i]);
+  float sum = 0.f;
+  for (int i = 0; i < nparts; ++i) sum += s[i] * expf(m[i] - mx);
+  const float l = mx + logf(sum);
+  if (lse) lse[r] = l;
+  if (out) {
+    const bool keep = ids[r] != 0 && tgt[r] > 0;
+    const float v = keep ? sign * (tl[r] - l) : 0.f;
+    out[r] = accumulate ? out[r] + v : v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_ROWS = 1024;
 __global__ void k_colsum_add(float* __restrict__ out, const float* __restrict__ X, int64_t rows, int cols, int64_t ldx) {
@@ -1037,6 +1057,10 @@ void lhood_accumulate(LaunchCtx& cx, const float* logits, const int32_t* tgt, co
   if (rows <= 0) return;
   k_lhood_accumulate<<<(int)rows, 256, 0, cx.stream>>>(logits, tgt, mask_ids, lh, V);
   check_launch(cx, "lhood_accumulate");
+}
+void vocab_lse_finish(LaunchCtx& cx, const float* part_max, const float* part_sum, int nparts, const float* tgt_logit,
+                      const int32_t* tgt, const int32_t* row_ids, float* lse, float* out, float sign, int accumulate, int64_t rows) {
+  L1D(k_vocab_lse_finish, rows, part_max, part_sum, nparts, tgt_logit, tgt, row_ids, lse, out, sign, accumulate, rows);
 }
 void clamp_adam(LaunchCtx& cx, float* W, float* dW, float* m, float* v, int64_t n, float step, float beta1, float beta2,
                 float eps, float grad_scale) {

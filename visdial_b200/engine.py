@@ -256,6 +256,9 @@ class Engine:
     def set_math_mode(self, mode: int):
         check(self.lib.vd_set_math_mode(self.h, mode))
 
+    def set_lazy_decout(self, on: bool):
+        check(self.lib.vd_set_lazy_decout(self.h, 1 if on else 0))
+
     def set_option_overlap(self, on: bool, reserve_sms: int = -1):
         check(self.lib.vd_set_option_overlap(self.h, int(on), int(reserve_sms)))
 

@@ -92,7 +92,12 @@ class Model:
         if encOutOnly:
             return encOut                                                  # :302
         if self.params["decoder"] == "gen":
-            decOut = self.decoder.forward(batch)                           # :313
+            # decOut only travels on to the criterion here: let the engine keep the (rows, V) log-probabilities on chip
+            self.engine.set_lazy_decout(True)
+            try:
+                decOut = self.decoder.forward(batch)                       # :313
+            finally:
+                self.engine.set_lazy_decout(False)
             curLoss = self.criterion.forward(decOut, batch)                # :314
             if not onlyForward:
                 gradCriterionOut = self.criterion.backward(decOut, batch)  # :318
