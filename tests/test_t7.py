@@ -88,3 +88,23 @@ def test_errors():
         t7.load(io.BytesIO(i32(4) + i32(1) + s_("V 1") + s_("nn.Linear")))  # a module: not in the schema
     with pytest.raises(t7.T7Error):
         t7.save(io.BytesIO(), {"x": object()})
+
+
+def test_reads_a_torch7_written_checkpoint():
+    """Pins t7.py against torch7's own serialiser and records the nngraph getParameters() order WHEN the artefacts exist
+    (tests/golden/external/README.md).  No LuaJIT / Torch7 in the build container."""
+    import os
+    import pytest
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "external")
+    path = os.path.join(here, "model_tiny.t7")
+    if not os.path.exists(path):
+        pytest.skip("external artefact model_tiny.t7 not present (see tests/golden/external/README.md)")
+    from visdial_b200 import t7
+    ck = t7.load(path)
+    assert "modelW" in ck and "modelParams" in ck
+    w = np.asarray(ck["modelW"])
+    assert w.ndim == 1 and w.dtype == np.float32 and np.isfinite(w).all()
+    order = os.path.join(here, "wrapper_params.txt")
+    if os.path.exists(order):
+        sizes = [int(np.prod([int(x) for x in line.split()[1].split("x")])) for line in open(order) if line.strip()]
+        assert sum(sizes) == w.size            # the flattened vector is the concatenation of wrapper:parameters() in that order
