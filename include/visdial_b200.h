@@ -160,6 +160,15 @@ int vd_gen_option_lhood(vd_engine* e, const vd_batch* b, const float** lhood_dev
 int vd_encoder_rnn_state(vd_engine* e, int32_t level, const float** h_last_dev, const float** c_last_dev);
 int vd_gen_decoder_step(vd_engine* e, int32_t rows, const int32_t* tokens_host, const float* const* h_prev,
                         const float* const* c_prev, const float** logp_dev, const float** h_out, const float** c_out);
+/* Beam search with the search state on the device (model.lua:510-570, all rounds of a dialog at once): one decoder step on
+ * `rows` hypotheses.  parent_host == NULL starts a search: init_h_host / init_c_host[2] are (rows, rnnHiddenSize) HOST arrays
+ * (model.lua:480-501).  Otherwise parent_host[r] >= 0 continues hypothesis r from the state row `parent` PRODUCED in the
+ * previous call, parent_host[r] < 0 from the state row (-1 - parent) was FED in the previous call (a beam column that received
+ * no candidate keeps its old content, :560-569).  Only the k best (log-prob, 0-based class) pairs of every row come back
+ * (torch.topk sorted; ties: lower class first) — the (rows, vocabSize) log-probabilities and the LSTM state stay in HBM. */
+int vd_gen_beam_step(vd_engine* e, int32_t rows, const int32_t* tokens_host, const int32_t* parent_host,
+                     const float* const* init_h_host, const float* const* init_c_host, int32_t k, float* topv_host,
+                     int32_t* topi_host);
 
 /* ---- optimiser step (model.lua:96-105 + optim_updates.lua:62-91) ---------------------------- */
 /* all-reduce(SUM)/world of dW when a communicator is attached, then clamp(-5,5), then adam.

@@ -239,6 +239,12 @@ def test_generate_answers_matches_oracle(enc):
     P = torch_params(params, flat)
     for conv in (0, 3, 7):
         got = model.generateAnswers(dl, "val", {"beamSize": 3, "beamLen": 6, "maxThreads": conv + 1}, strict=False)[conv]["dialog"]
+        # the batched search (all rounds per step, state + log-probabilities on the device, top-k on the device) walks exactly
+        # the hypotheses of the reference-structured loop (one round at a time, everything through the host)
+        host = model.generateAnswers(dl, "val", {"beamSize": 3, "beamLen": 6, "maxThreads": conv + 1, "hostBeam": 1},
+                                     strict=False)[conv]["dialog"]
+        assert [None if g is None else (g["answer"], g["length"], g["score"]) for g in got] == \
+               [None if h is None else (h["answer"], h["length"], h["score"]) for h in host]
         tb = torch_batch(orc.get_index_data(np.array([conv])))
         with torch.no_grad():
             want = O.generate_answers(O.Ctx(), params, P, tb, V - 1, V, beam_size=3, beam_len=6, strict=False)

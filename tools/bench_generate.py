@@ -28,7 +28,11 @@ m.generateAnswers(dl, "val", {"beamSize": 5, "beamLen": 20, "maxThreads": 1}, st
 t0 = time.perf_counter()
 out = m.generateAnswers(dl, "val", {"beamSize": 5, "beamLen": 20, "maxThreads": nd}, strict=False)
 dt = time.perf_counter() - t0
+t0 = time.perf_counter()
+m.generateAnswers(dl, "val", {"beamSize": 5, "beamLen": 20, "maxThreads": max(1, nd // 2), "hostBeam": 1}, strict=False)
+dt_host = (time.perf_counter() - t0) / max(1, nd // 2)
 done = sum(1 for d in out for r in d["dialog"] if r is not None)
 print(json.dumps({"encoder": enc, "dialogs": nd, "ms_per_dialog": dt / nd * 1e3, "ms_per_round": dt / nd / 10 * 1e3,
-                  "rounds_with_a_finished_beam": done, "beamSize": 5, "beamLen": 20, "vocabSize": 10000}))
+                  "rounds_with_a_finished_beam": done,
+                  "ms_per_dialog_reference_structure": dt_host * 1e3, "beamSize": 5, "beamLen": 20, "vocabSize": 10000}))
 dl.close(); m.engine.close()

@@ -243,6 +243,12 @@ int vd_gen_decoder_step(vd_engine* h, int32_t rows, const int32_t* tokens_host, 
   })
 }
 
+int vd_gen_beam_step(vd_engine* h, int32_t rows, const int32_t* tokens_host, const int32_t* parent_host,
+                     const float* const* init_h_host, const float* const* init_c_host, int32_t k, float* topv_host,
+                     int32_t* topi_host) {
+  VD_TRY({ ENG(h)->gen_beam_step(rows, tokens_host, parent_host, init_h_host, init_c_host, k, topv_host, topi_host); })
+}
+
 int vd_clamp_adam_step(vd_engine* h, float lr) { VD_TRY({ ENG(h)->clamp_adam_step(lr); }) }
 
 int vd_comm_unique_id(void* id_out) { VD_TRY({ NOTNULL(id_out); vd::comm_unique_id(id_out); }) }

@@ -1342,6 +1342,48 @@ void Engine::gen_decoder_step(int64_t rows, const int32_t* tokens_host, const fl
   logsoftmax_rows(cx, gstep_logp, tok, rows, V);                // gen.lua:23-24 (MaskZero)
 }
 
+// One beam-search step (model.lua:510-570) for `rows` hypotheses at once (all rounds of a dialog x beamSize).  The state of
+// the previous call stays on the device: parent_host[r] >= 0 takes the state hypothesis parent produced, < 0 the state row
+// (-1 - parent) was fed (stale beam column).  parent_host == NULL starts a search from the host arrays init_h / init_c.
+void Engine::gen_beam_step(int64_t rows, const int32_t* tokens_host, const int32_t* parent_host, const float* const* init_h_host,
+                           const float* const* init_c_host, int k, float* topv_host, int32_t* topi_host) {
+  VD_REQUIRE(cfg.dec == DEC_GEN && have_fwd, VD_E_STATE, "gen_beam_step needs the gen decoder after encoder_forward");
+  VD_REQUIRE(rows > 0 && tokens_host && topv_host && topi_host && k >= 1 && k <= cfg.V, VD_E_BADARG, "rows / tokens / k");
+  VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
+  cx.stream = main_stream;
+  const int H = cfg.H;
+  float* hp[2]; float* cp[2];
+  for (int l = 0; l < 2; ++l) { hp[l] = arena.get<float>(rows * H); cp[l] = arena.get<float>(rows * H); }
+  if (!parent_host) {
+    VD_REQUIRE(init_h_host && init_c_host, VD_E_BADARG, "first beam step needs the initial state");
+    for (int l = 0; l < 2; ++l) {
+      VD_CUDA_CHECK(cudaMemcpyAsync(hp[l], init_h_host[l], (size_t)rows * H * sizeof(float), cudaMemcpyHostToDevice, cx.stream));
+      VD_CUDA_CHECK(cudaMemcpyAsync(cp[l], init_c_host[l], (size_t)rows * H * sizeof(float), cudaMemcpyHostToDevice, cx.stream));
+    }
+  } else {
+    VD_REQUIRE(beam_rows == rows && beam_in_h[0], VD_E_STATE, "gen_beam_step: no previous step with this many rows");
+    int32_t* par = arena.get<int32_t>(rows);
+    VD_CUDA_CHECK(cudaMemcpyAsync(par, parent_host, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
+    const float* out_h[2] = {gstep1.h, gstep2.h};
+    const float* out_c[2] = {gstep1.c, gstep2.c};
+    for (int l = 0; l < 2; ++l) {
+      beam_gather(cx, hp[l], out_h[l], beam_in_h[l], par, rows, H);
+      beam_gather(cx, cp[l], out_c[l], beam_in_c[l], par, rows, H);
+    }
+  }
+  const float* hpc[2] = {hp[0], hp[1]};
+  const float* cpc[2] = {cp[0], cp[1]};
+  gen_decoder_step(rows, tokens_host, hpc, cpc);            // synchronises once for the token upload
+  for (int l = 0; l < 2; ++l) { beam_in_h[l] = hp[l]; beam_in_c[l] = cp[l]; }
+  beam_rows = rows;
+  float* tv = arena.get<float>(rows * k);
+  int32_t* ti = arena.get<int32_t>(rows * k);
+  topk_rows(cx, gstep_logp, rows, cfg.V, k, tv, ti);
+  VD_CUDA_CHECK(cudaMemcpyAsync(topv_host, tv, (size_t)rows * k * sizeof(float), cudaMemcpyDeviceToHost, cx.stream));
+  VD_CUDA_CHECK(cudaMemcpyAsync(topi_host, ti, (size_t)rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+  VD_CUDA_CHECK(cudaStreamSynchronize(cx.stream));
+}
+
 // model.lua:96-99 + optim_updates.lua:62-91
 void Engine::clamp_adam_step(float lr) {
   VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));

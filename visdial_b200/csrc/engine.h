@@ -220,6 +220,12 @@ struct Engine {
   LstmRun gstep1, gstep2;
   float* gstep_logp = nullptr;
   void gen_decoder_step(int64_t rows, const int32_t* tokens_host, const float* const* h_prev, const float* const* c_prev);
+  // beam search with the decoder state and the (rows, V) log-probabilities kept on the device: per step only the tokens and
+  // parent indices go up and the k best (log-prob, class) pairs per hypothesis come down
+  const float *beam_in_h[2] = {nullptr, nullptr}, *beam_in_c[2] = {nullptr, nullptr};
+  int64_t beam_rows = 0;
+  void gen_beam_step(int64_t rows, const int32_t* tokens_host, const int32_t* parent_host, const float* const* init_h_host,
+                     const float* const* init_c_host, int k, float* topv_host, int32_t* topi_host);
   void clamp_adam_step(float lr);
   void allreduce_grads();
   // Overlapped gradient sync (world > 1): dW is all-reduced in buckets on `comm_stream` as soon as each bucket's last

@@ -120,6 +120,10 @@ void nll_bwd(LaunchCtx& cx, const float* logp, const int32_t* tgt, const int32_t
 void lhood_accumulate(LaunchCtx& cx, const float* logits, const int32_t* tgt, const int32_t* mask_ids, float* lh,
                       int64_t rows, int V);
 
+// beam search on the device (model.lua:510-570): k best classes per row (value desc, index asc); state shuffle by parent index
+void topk_rows(LaunchCtx& cx, const float* x, int64_t rows, int V, int k, float* topv, int32_t* topi);
+void beam_gather(LaunchCtx& cx, float* dst, const float* out_prev, const float* in_prev, const int32_t* parent, int64_t rows, int H);
+
 // ---- optimiser (model.lua:96-99, optim_updates.lua:62-91) ------------------------------------------
 void clamp_adam(LaunchCtx& cx, float* W, float* dW, float* m, float* v, int64_t n, float step, float beta1,
                 float beta2, float eps, float grad_scale);

@@ -1,5 +1,6 @@
 // HBM-/latency-bound kernels of the hot path: everything that is not a dense contraction.
 // Coalesced, float4-vectorised where the layout allows, warp-shuffle reductions.
+#include "../../include/visdial_b200.h"
 #include "kernels.cuh"
 
 namespace vd {
@@ -205,6 +206,54 @@ __global__ void k_lstm_pw_bwd(const float* __restrict__ gates, const float* __re
   d[2 * H + j] = dh * tc * go * (1.f - go);
   d[3 * H + j] = dc * gi * (1.f - gg * gg);
   dc_carry[idx] = dc * gf;
+}
+
+// ---- beam search on the device (model.lua:510-570): the k best continuations of every hypothesis, and the state shuffle
+// Total order of torch.topk(sorted) with the pinned tie rule: value descending, class index ascending.  Round r of the loop
+// finds the greatest element strictly AFTER the previous winner in that order, so no "taken" flags are needed.
+__global__ void __launch_bounds__(256) k_topk_rows(const float* __restrict__ x, int V, int k, float* __restrict__ topv,
+                                                   int32_t* __restrict__ topi) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ float wv; __shared__ int wi;
+  const float* row = x + (int64_t)blockIdx.x * V;
+  float pv = INFINITY; int pi = -1;
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+      const float v = row[c];
+      const bool after = v < pv || (v == pv && c > pi);
+      if (after && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+      wv = bv; wi = bi;
+      topv[(int64_t)blockIdx.x * k + r] = bv;
+      topi[(int64_t)blockIdx.x * k + r] = bi;
+    }
+    __syncthreads();
+    pv = wv; pi = wi;
+    __syncthreads();
+  }
+}
+// next step's previous state of row r: parent >= 0 -> the state hypothesis `parent` PRODUCED in the last step; parent < 0 -> the
+// state row (-1 - parent) was FED in the last step (a beam column that received no candidate keeps its old content, model.lua:560-569)
+__global__ void k_beam_gather(float* __restrict__ dst, const float* __restrict__ out_prev, const float* __restrict__ in_prev,
+                              const int32_t* __restrict__ parent, int64_t rows, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const int64_t r = i / H; const int c = (int)(i % H);
+  const int p = parent[r];
+  dst[i] = p >= 0 ? out_prev[(int64_t)p * H + c] : in_prev[(int64_t)(-1 - p) * H + c];
 }
 
 // row log-sum-exp from the per-slice partials of the fused vocabulary projection, then the criterion / likelihood term
@@ -1061,6 +1110,15 @@ void lhood_accumulate(LaunchCtx& cx, const float* logits, const int32_t* tgt, co
 void vocab_lse_finish(LaunchCtx& cx, const float* part_max, const float* part_sum, int nparts, const float* tgt_logit,
                       const int32_t* tgt, const int32_t* row_ids, float* lse, float* out, float sign, int accumulate, int64_t rows) {
   L1D(k_vocab_lse_finish, rows, part_max, part_sum, nparts, tgt_logit, tgt, row_ids, lse, out, sign, accumulate, rows);
+}
+void topk_rows(LaunchCtx& cx, const float* x, int64_t rows, int V, int k, float* topv, int32_t* topi) {
+  VD_REQUIRE(k >= 1 && k <= V, VD_E_BADARG, "topk_rows: k");
+  if (rows == 0) return;
+  k_topk_rows<<<(unsigned)rows, 256, 0, cx.stream>>>(x, V, k, topv, topi);
+  check_launch(cx, "k_topk_rows");
+}
+void beam_gather(LaunchCtx& cx, float* dst, const float* out_prev, const float* in_prev, const int32_t* parent, int64_t rows, int H) {
+  L1D(k_beam_gather, rows * H, dst, out_prev, in_prev, parent, rows, H);
 }
 void clamp_adam(LaunchCtx& cx, float* W, float* dW, float* m, float* v, int64_t n, float step, float beta1, float beta2,
                 float eps, float grad_scale) {

@@ -216,7 +216,64 @@ class Model:
                         eng.upload(state_buf[i], a[:n])
                     return eng.gen_decoder_step(tokens, state_buf[0:2], state_buf[2:4])
 
-                if not sampleWords:
+                if not sampleWords and not params.get("hostBeam"):
+                    # All N rounds of the dialog are searched at once (N * beamSize hypotheses per decoder step).  The LSTM state
+                    # and the (rows, V) log-probabilities stay on the device (vd_gen_beam_step): per step the tokens and parent
+                    # indices go up, the beamSize best (log-prob, class) pairs of every hypothesis come down; the candidate merge
+                    # of model.lua:529-569 — including its quirks — runs on those few numbers.
+                    bs = beamSize
+                    beams = np.zeros((N, beamLen, bs), dtype=np.int64)                  # :479
+                    beams[:, 0, :] = startToken                                         # :506
+                    scores = np.zeros((N, bs), dtype=np.float64)                        # :507
+                    finish = [[] for _ in range(N)]                                     # :508
+                    if has_layers:                                                      # :482-491
+                        iH = [np.repeat(encH[0][0], bs, 0), np.repeat(encOut, bs, 0)]
+                        iC = [np.repeat(encH[0][1], bs, 0), np.repeat(encH[1][1], bs, 0)]
+                    else:                                                               # :493-501
+                        z = np.zeros((N * bs, H), np.float32)
+                        iH, iC = [z, np.repeat(encOut, bs, 0)], [z, z]
+                    parent = None
+                    for stp in range(1, beamLen):                                       # :510
+                        topv, topi = eng.gen_beam_step(beams[:, stp - 1, :].reshape(-1), parent, iH, iC, bs)   # :519-542
+                        parent = -1 - np.arange(N * bs, dtype=np.int32)                 # default: the column keeps its old content
+                        exploreSize = 1 if stp == 1 else bs                             # :516
+                        for it in range(N):
+                            cands = []
+                            for wordId in range(exploreSize):                           # :529
+                                r = it * bs + wordId
+                                for candId in range(bs):                                # :544
+                                    tok = int(topi[r, candId]) + 1
+                                    sc = float(scores[it, wordId]) + float(topv[r, candId])
+                                    if tok == endToken:                                 # :548
+                                        cb = beams[it, :, wordId].copy()
+                                        cb[stp] = tok
+                                        finish[it].append({"beam": cb, "length": stp + 1, "score": sc})
+                                    else:
+                                        cands.append((sc, wordId, tok))
+                            cands.sort(key=lambda t: -t[0])                             # :558 (stable)
+                            old = beams[it].copy()
+                            for candId in range(min(len(cands), bs)):                   # :560-569
+                                sc, wordId, tok = cands[candId]
+                                beams[it, :, candId] = old[:, wordId]
+                                beams[it, stp, candId] = tok
+                                scores[it, candId] = sc
+                                parent[it * bs + candId] = it * bs + wordId
+                    for it in range(N):
+                        finish[it].sort(key=lambda d: -d["score"])                      # :572
+                        if not finish[it]:
+                            if strict:
+                                raise IndexError("no beam reached <END> within beamLen (model.lua:575 indexes nil here)")
+                            threadAnswers.append(None)
+                            continue
+                        best = finish[it][0]
+                        entry = {"question": ques[it].tolist(), "answer": best["beam"].tolist(), "score": best["score"],
+                                 "length": best["length"]}
+                        if words:
+                            entry["question_text"], entry["answer_text"] = words(ques[it]), words(best["beam"])
+                        threadAnswers.append(entry)
+                elif not sampleWords:
+                    # the reference's own loop structure (one round at a time, log-probabilities and state through the host):
+                    # kept as the cross-check of the batched search above (params.hostBeam = 1)
                     for it in range(N):                                                 # :472
                         beams = np.zeros((beamLen, beamSize), dtype=np.int64)           # :479
                         if has_layers:                                                  # :482-491
