@@ -264,7 +264,7 @@ def run_reference(args):
         return
     arm = CpuArm(args.config)
     cfgB = CONFIGS[args.config]["batch"] if args.batch <= 0 else args.batch
-    probeB = min(cfgB, 4)
+    probeB = min(cfgB, 8)
     if args.cpu_threads > 0:
         threads, table = min(args.cpu_threads, os.cpu_count() or 1), {}
         arm.torch.set_num_threads(threads)
@@ -606,7 +606,7 @@ def main():
     ap.add_argument("--math", default="f16", choices=["f16", "tf32", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=8, help="dialogs of the bounded cpu_baseline sample in the GPU arm's line")
     ap.add_argument("--ref-batch", type=int, default=0, help="dialogs per reference step (0 = the GPU arm's batch if the run fits --ref-budget-s, else 8)")
-    ap.add_argument("--ref-budget-s", type=float, default=420.0, help="time budget of the whole --impl reference run")
+    ap.add_argument("--ref-budget-s", type=float, default=900.0, help="time budget of the whole --impl reference run")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = pick by a sweep over 8/16/32/64/128 threads")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="reference arm: skip the batched-CPU figure")
