@@ -511,6 +511,13 @@ def run_ours(args, rank, local, world):
                     "achieved_in_overlapped_step": (sum(stats_shared[k]["flops"] for k in LSTM_STEP_KEYS) /
                                                     max(sum(stats_shared[k]["ms"] for k in LSTM_STEP_KEYS) * 1e-3, 1e-12) / 1e12),
                     "executed_flop_per_launch": fl / max(n_l, 1), "traffic": None}
+        # SURVEY.md §8(d) convention (algorithmic FLOP: the forward step is credited with the D = embedSize x-projection
+        # 2*R*4H*(H+D) although it executes as a table gather) — reported NEXT TO the executed figure, never instead of it
+        R_opt = B * p["maxQuesCount"] * p["numOptions"]
+        fl_conv = fl + stats["lstm_step"]["launches"] * 2.0 * R_opt * 4 * p["rnnHiddenSize"] * p["embedSize"]
+        roofline["achieved_survey_convention"] = fl_conv / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        roofline["frac_survey_convention"] = roofline["achieved_survey_convention"] / peak
+        roofline["algorithmic_flop_per_launch_survey_convention"] = fl_conv / max(n_l, 1)
         tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             t = json.load(open(tpath)).get(args.math)
