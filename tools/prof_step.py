@@ -17,6 +17,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--config", default="C4")
 ap.add_argument("--overlap", type=int, default=1)
+ap.add_argument("--warmup", type=int, default=0)
 a = ap.parse_args()
 p = bench.config_params(a.config)
 p["batchSize"] = a.batch
@@ -31,6 +32,9 @@ class L:
         return b
 
 
+for _ in range(a.warmup):
+    m.trainIteration(L())
+m.engine.synchronize()
 m.engine.timer_start()
 for _ in range(a.steps):
     m.trainIteration(L())
