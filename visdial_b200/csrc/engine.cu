@@ -1066,7 +1066,9 @@ void Engine::options_forward_async() {
   if (opt_overlap) {                                                // leave SMs to the encoder's concurrent chains
     static int fwd_reserve = -1;                                    // VD_OPT_RESERVE_FWD: A/B knob, default = the common reserve
     if (fwd_reserve < 0) { const char* e = getenv("VD_OPT_RESERVE_FWD"); fwd_reserve = e ? (atoi(e) & ~1) : 1 << 20; }
-    cx.sm_budget = cx.sm_count - (fwd_reserve == 1 << 20 ? opt_reserve_sms : std::min(fwd_reserve, cx.sm_count - 16));
+    // with the persistent encoder forward (VD_MATH_F16) nothing latency-bound runs beside the option stream's forward: no reserve
+    const int dflt = (math_mode == VD_MATH_F16 && enc_persist_enabled()) ? 0 : opt_reserve_sms;
+    cx.sm_budget = cx.sm_count - (fwd_reserve == 1 << 20 ? dflt : std::min(fwd_reserve, cx.sm_count - 16));
   }
   ids_o = arena.get<int32_t>(Ro * db.To);
   transpose_ids(cx, db.options, ids_o, Ro, db.To);
