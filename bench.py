@@ -494,30 +494,39 @@ def run_ours(args, rank, local, world):
         per = {k: {"launches": stats[k]["launches"], "avg_launch_ms": stats[k]["ms"] / max(stats[k]["launches"], 1),
                    "TFLOP/s": stats[k]["flops"] / max(stats[k]["ms"] * 1e-3, 1e-12) / 1e12,
                    "algorithmic_GB/s": stats[k]["bytes"] / max(stats[k]["ms"] * 1e-3, 1e-12) / 1e9} for k in LSTM_STEP_KEYS}
-        roofline = {"bound": "tensor",
-                    "kernel": ("k_lstm16<fwd|bwd>: option-LSTM step, fp16 operands (recurrent gate GEMM on tcgen05 kind::f16, CTA pairs, "
-                               "fp32 TMEM accumulators + SeqLSTM pointwise epilogue)" if f16 else
-                               "k_tc_gemm<256,LSTM_FWD|LSTM_BWD,2>: option-LSTM step (recurrent gate GEMM on tcgen05 kind::tf32 + SeqLSTM "
-                               "pointwise epilogue)") + ", %d launches per training step" % (n_l // args.steps),
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "flops_counted": "executed tensor-core FLOP only (2*R*4H*H per launch): the gathered x-projection and the K=0 first/"
-                                     "last steps are not credited",
-                    "peak_source": "%s bf16_tflops_sustained%s" % (peaks["src"], "" if f16 else " / 2 (TF32 operands)"),
-                    "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / max(ms_iso, 1e-9),
-                    "per_direction": per,
-                    "hbm_algorithmic_GB/s": by / max(t_ms * 1e-3, 1e-12) / 1e9, "hbm_frac_of_measured_peak": by / max(t_ms * 1e-3, 1e-12) / 1e9 / peaks["hbm"],
-                    "measured_in": "a second pass of the same %d steps with the option stream serialised behind the encoder "
-                                   "(%.3f ms/step), CUDA events around every launch of this kernel class on its stream" % (args.steps, ms_iso / args.steps),
-                    "achieved_in_overlapped_step": (sum(stats_shared[k]["flops"] for k in LSTM_STEP_KEYS) /
-                                                    max(sum(stats_shared[k]["ms"] for k in LSTM_STEP_KEYS) * 1e-3, 1e-12) / 1e12),
-                    "executed_flop_per_launch": fl / max(n_l, 1), "traffic": None}
+        hbm_gbs = by / max(t_ms * 1e-3, 1e-12) / 1e9
+        kernel_desc = ("k_lstm16<fwd|bwd>: option-LSTM step, fp16 operands (recurrent gate GEMM on tcgen05 kind::f16, CTA pairs, "
+                       "fp32 TMEM accumulators + SeqLSTM pointwise epilogue)" if f16 else
+                       "k_tc_gemm<256,LSTM_FWD|LSTM_BWD,2>: option-LSTM step (recurrent gate GEMM on tcgen05 kind::tf32 + SeqLSTM "
+                       "pointwise epilogue)") + ", %d launches per training step" % (n_l // args.steps)
         # SURVEY.md §8(d) convention (algorithmic FLOP: the forward step is credited with the D = embedSize x-projection
         # 2*R*4H*(H+D) although it executes as a table gather) — reported NEXT TO the executed figure, never instead of it
         R_opt = B * p["maxQuesCount"] * p["numOptions"]
         fl_conv = fl + stats["lstm_step"]["launches"] * 2.0 * R_opt * 4 * p["rnnHiddenSize"] * p["embedSize"]
-        roofline["achieved_survey_convention"] = fl_conv / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
-        roofline["frac_survey_convention"] = roofline["achieved_survey_convention"] / peak
-        roofline["algorithmic_flop_per_launch_survey_convention"] = fl_conv / max(n_l, 1)
+        conv = fl_conv / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        tensor = {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                  "flops_counted": "executed tensor-core FLOP only (2*R*4H*H per launch): the gathered x-projection and the K=0 first/"
+                                   "last steps are not credited",
+                  "peak_source": "%s bf16_tflops_sustained%s" % (peaks["src"], "" if f16 else " / 2 (TF32 operands)"),
+                  "executed_flop_per_launch": fl / max(n_l, 1),
+                  "achieved_survey_convention": conv, "frac_survey_convention": conv / peak,
+                  "achieved_in_overlapped_step": (sum(stats_shared[k]["flops"] for k in LSTM_STEP_KEYS) /
+                                                  max(sum(stats_shared[k]["ms"] for k in LSTM_STEP_KEYS) * 1e-3, 1e-12) / 1e12)}
+        hbm = {"achieved": hbm_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm"],
+               "bytes_counted": "algorithmic HBM bytes per launch (DESIGN.md §9): forward fp16 gates out + fp32 c in/out + fp16 h in/out = "
+                                "10 KB per option row (the fp16 projection-table gather is L2-resident, not counted); backward fp16 gates "
+                                "in + fp16 da in/out + fp32 c_{t-1}, c_t in + fp32 dc in/out = 20 KB per row",
+               "peak_source": "%s hbm_gbs (MEASURED_PEAKS.json)" % peaks["src"], "algorithmic_bytes_per_launch": by / max(n_l, 1)}
+        # VD_MATH_F16: the class sits nearer the HBM roof than the tensor roof (ncu: backward step DRAM 61 % / tensor 31 %, forward
+        # 40 % / 34 %), so HBM is the binding roofline; the TF32 kernels are nearer their (assumed) tensor roof.  Both are always given.
+        head = hbm if f16 else tensor
+        roofline = {"bound": "hbm" if f16 else "tensor", "kernel": kernel_desc,
+                    "achieved": head["achieved"], "peak": head["peak"], "unit": head["unit"], "frac": head["frac"],
+                    "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / max(ms_iso, 1e-9),
+                    "per_direction": per, "hbm": hbm, "tensor": tensor,
+                    "measured_in": "a second pass of the same %d steps with the option stream serialised behind the encoder "
+                                   "(%.3f ms/step), CUDA events around every launch of this kernel class on its stream" % (args.steps, ms_iso / args.steps),
+                    "traffic": None}
         tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             t = json.load(open(tpath)).get(args.math)

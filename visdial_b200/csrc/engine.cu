@@ -419,7 +419,8 @@ void Engine::lstm_forward_step(LstmRun& r, int t) {
       LaunchCtx::Scope sc(&cx, "lstm_step_first", 0.0, R * (2.0 * G + 2.0 * G + 6.0 * H));
       lstm16_first_step(cx, R, H, r.P16, tok, bias, cp, mk, g16, r.c + slot * R * H, r.h16 + slot * R * H, h32);
     } else {
-      LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * H, R * (2.0 * G + 2.0 * G + 4.0 * H + 4.0 * H + 2.0 * H + 2.0 * H));
+      // algorithmic HBM bytes: fp16 gates out, fp32 c in + out, fp16 h in + out (the fp16 table gather is L2-resident: not counted)
+      LaunchCtx::Scope sc(&cx, "lstm_step", 2.0 * R * G * H, R * (2.0 * G + 4.0 * H + 4.0 * H + 2.0 * H + 2.0 * H));
       lstm16_step_fwd(cx, R, H, r.h16 + pslot * R * H, r.Wh16, r.P16, tok, bias, cp, mk, g16, r.c + slot * R * H,
                       r.h16 + slot * R * H, h32);
     }
