@@ -5,6 +5,8 @@
 #include "engine.h"
 #include <dlfcn.h>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 
 namespace vd {
 namespace {
@@ -19,6 +21,8 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -36,6 +40,8 @@ NcclApi& api() {
   a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(a.handle, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.handle, "ncclGroupEnd");
   VD_REQUIRE(a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy, VD_E_COMM, "libnccl lacks required symbols");
   return a;
 }
@@ -63,6 +69,8 @@ void comm_init(Engine* e, const void* idbytes, int rank, int world) {
   if (world == 1) return;
   ncclUniqueId id;
   memcpy(&id, idbytes, sizeof(id));
+  // VD_NCCL_MAX_NCHANNELS=n: cap the SMs the overlapped all-reduce takes from the backward pass (A/B knob; unset = NCCL's choice)
+  if (const char* ch = getenv("VD_NCCL_MAX_NCHANNELS")) setenv("NCCL_MAX_NCHANNELS", ch, 0);
   ncclComm_t comm;
   nccl_check(api().CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
   e->nccl_comm = comm;
@@ -127,6 +135,9 @@ void Engine::reduce_remaining() {
   join_options_backward();
   if (seg_reduced.size() != lay.segs.size()) seg_reduced.assign(lay.segs.size(), 0);
   const int n = (int)lay.segs.size();
+  // the segments still local (at least the word embedding, which every branch writes; with the option stream also opt.lstm,
+  // final at the same moment) go out as ONE grouped launch: one collective latency at the exposed end of the step
+  std::vector<std::pair<int64_t, int64_t>> runs;
   for (int i = 0; i < n;) {
     if (seg_reduced[i]) { ++i; continue; }
     int j = i;
@@ -134,8 +145,14 @@ void Engine::reduce_remaining() {
     for (int k = i; k <= j; ++k) seg_reduced[k] = 1;
     const int64_t off = lay.segs[i].off;
     const int64_t end = j + 1 < n ? lay.segs[j + 1].off : nparams;
-    reduce_range(off, end - off, main_stream, nullptr);
+    runs.emplace_back(off, end - off);
     i = j + 1;
+  }
+  if (!runs.empty()) {
+    const bool grouped = runs.size() > 1 && api().GroupStart && api().GroupEnd;
+    if (grouped) nccl_check(api().GroupStart(), "ncclGroupStart");
+    for (size_t r = 0; r < runs.size(); ++r) reduce_range(runs[r].first, runs[r].second, main_stream, nullptr);
+    if (grouped) nccl_check(api().GroupEnd(), "ncclGroupEnd");
   }
   if (comm_pending) {
     VD_CUDA_CHECK(cudaEventRecord(ev_comm_done, comm_stream));

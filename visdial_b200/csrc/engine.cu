@@ -1013,10 +1013,9 @@ void Engine::encoder_backward(const float* dEnc) {
     }
   }
   join_side();
-  // bucket 4: the option LSTM's weights, behind the option stream's last kernel (issued last in host order so that it
-  // does not queue ahead of the encoder's buckets on the communication stream); what is left — the word embedding,
-  // which every branch writes, and the small layers not covered above — goes in clamp_adam_step
-  if (opt_bwd_pending) reduce_segments(seg("opt.lstm.weight"), (int)lay.segs.size() - 1, nullptr, ev_opt_done);
+  // what is left — the option LSTM's weights (final when the option stream ends, i.e. now), the word embedding, which every
+  // branch writes, and the small layers not covered above — goes in clamp_adam_step
+  // (opt.lstm, final at the same moment, goes out with the embedding in the grouped launch of reduce_remaining)
   join_options_backward();
 }
 
