@@ -292,6 +292,218 @@ k_enc_pair_fwd(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BPTT of the pair, same structure mirrored in time and in roles:
+//   layer-2 CTA (slice of 32 hidden units): dh2_t = da2_{t+1} Wh2            (K = 4H)  [+ dL/dh2 at the last step]
+//   layer-1 CTA (slice of 16 hidden units): dh1_t = da2_t Wx2 + da1_{t+1} Wh1 (K = 8H)  [+ dL/dh1 at the last step]
+// then the SeqLSTM backward pointwise (saved gates, c_{t-1}, c_t; dc carried in registers) -> da_t as fp32 (what the weight /
+// input gradients after the kernel read) and fp16 (the A operand of the steps that follow).  Layer 2 runs ahead of layer 1;
+// layer 1's producer streams the da2_t half first (ready early) and the da1_{t+1} half when its own previous step is published.
+struct EncBwdParams {
+  int T, R, H, RB;
+  int nS1, nS2, groups;            // slices of layer 1 (H/16), layer 2 (H/32)
+  const float* gates1; const float* c1; float* da1; __half* da1_16;
+  const float* gates2; const float* c2; float* da2; __half* da2_16;
+  const float* dh_last1; const float* dc_last1; const float* dh_last2; const float* dc_last2;   // (R,H) each or null
+  const int32_t* mask;
+  int* flags;                      // [2][RB][T]
+};
+
+__global__ void __launch_bounds__(EP_THREADS, 1)
+k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const EncBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem;
+  uint8_t* stages = smem + EP_W_BYTES_MAX;
+  uint64_t* full = (uint64_t*)(stages + EP_STAGES * EP_STAGE_BYTES);
+  uint64_t* empty = full + EP_STAGES;
+  uint64_t* tfull = empty + EP_STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint64_t* wbar = tempty + 1;
+  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, T = p.T;
+  const int per_group = p.nS1 + p.nS2;
+  const int group = blockIdx.x / per_group, idx = blockIdx.x % per_group;
+  const int layer = idx < p.nS2 ? 1 : 0;                  // 1 = layer 2 (top), 0 = layer 1
+  const int slice = layer == 1 ? idx : idx - p.nS2;
+  const int HS = layer == 1 ? 32 : 16;                    // hidden units (= accumulator columns) of this slice
+  const int KBP = 4 * H / 64;                             // k-blocks of one (rows, 4H) da panel
+  const int KBW = layer == 1 ? KBP : 2 * KBP;             // k-blocks of the resident weight slice
+  int* flag1 = p.flags;
+  int* flag2 = p.flags + (size_t)p.RB * T;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < EP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 4); mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)(KBW * HS * 128));
+      for (int kb = 0; kb < KBW; ++kb)
+        tma_load_2d(wsm + kb * HS * 128, layer == 1 ? &tmW2 : &tmW1, wbar, kb * 64, slice * HS);
+      int s = 0; uint32_t ph = 0;
+      auto load_panel = [&](const CUtensorMap* tm, int row0) {
+        for (int kb = 0; kb < KBP; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], EP_STAGE_BYTES);
+          tma_load_2d(stages + s * EP_STAGE_BYTES, tm, &full[s], kb * 64, row0);
+          if (++s == EP_STAGES) { s = 0; ph ^= 1; }
+        }
+      };
+      for (int rb = group; rb < p.RB; rb += p.groups) {
+        for (int t = T - 1; t >= 0; --t) {
+          if (layer == 1) {
+            if (t == T - 1) continue;
+            wait_flag(flag2 + (size_t)rb * T + (t + 1), p.nS2);
+            load_panel(&tmA2, (t + 1) * p.R + rb * 128);
+          } else {
+            wait_flag(flag2 + (size_t)rb * T + t, p.nS2);            // da2_t: the layer above is ahead
+            load_panel(&tmA2, t * p.R + rb * 128);
+            if (t < T - 1) {
+              wait_flag(flag1 + (size_t)rb * T + (t + 1), p.nS1);
+              load_panel(&tmA1, (t + 1) * p.R + rb * 128);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ep_idesc_f16(128, HS);
+    mbar_wait(wbar, 0);
+    tc_fence_after();
+    int s = 0; uint32_t ph = 0; uint32_t nuse = 0;
+    for (int rb = group; rb < p.RB; rb += p.groups) {
+      for (int t = T - 1; t >= 0; --t) {
+        const int npan = layer == 1 ? (t < T - 1 ? 1 : 0) : (t < T - 1 ? 2 : 1);
+        if (npan == 0) continue;
+        mbar_wait(tempty, (nuse & 1) ^ 1);
+        tc_fence_after();
+        ++nuse;
+        uint32_t first = 1;
+        for (int pan = 0; pan < npan; ++pan) {
+          const int kb0 = pan * KBP;                       // layer 1: panel 0 = Wx2 half, panel 1 = Wh1 half; layer 2: Wh2
+          for (int kb = 0; kb < KBP; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = smem_u32(stages + s * EP_STAGE_BYTES);
+              const uint32_t sb = smem_u32(wsm + (kb0 + kb) * HS * 128);
+              const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                ep_umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(&empty[s]);
+              if (pan == npan - 1 && kb == KBP - 1) umma_commit(tfull);
+            }
+            __syncwarp();
+            first = 0;
+            if (++s == EP_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int j0 = slice * HS;
+    const float* gates = layer == 1 ? p.gates2 : p.gates1;
+    const float* cst = layer == 1 ? p.c2 : p.c1;
+    float* da = layer == 1 ? p.da2 : p.da1;
+    __half* da16 = layer == 1 ? p.da2_16 : p.da1_16;
+    const float* dh_last = layer == 1 ? p.dh_last2 : p.dh_last1;
+    const float* dc_last = layer == 1 ? p.dc_last2 : p.dc_last1;
+    int* flag = layer == 1 ? flag2 : flag1;
+    uint32_t nuse = 0;
+    for (int rb = group; rb < p.RB; rb += p.groups) {
+      const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
+      const bool row_ok = row < p.R;
+      float dc[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) dc[e] = 0.f;
+      for (int t = T - 1; t >= 0; --t) {
+        const bool has_acc = layer == 0 || t < T - 1;
+        const int64_t tr = (int64_t)t * p.R + row;
+        const float keep = (row_ok && p.mask && p.mask[tr] == 0) ? 0.f : 1.f;
+        const int nsub = HS / 8;
+        if (has_acc) { mbar_wait(tfull, nuse & 1); tc_fence_after(); ++nuse; }
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          if (sub < nsub) {
+            float dh[8], g[4][8], cp[8], cc[8], out[4][8];
+            if (has_acc) { tmem_ld8(taddr + sub * 8, dh); tmem_ld_wait(); }
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dh[e] = 0.f;
+            }
+            const int j = j0 + sub * 8;
+            if (row_ok) {
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) ld8g(gates + tr * 4 * H + gg * H + j, g[gg]);
+              ld8g(cst + tr * H + j, cc);
+              if (t > 0) ld8g(cst + (tr - p.R) * H + j, cp);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+              }
+              if (t == T - 1) {
+                if (dh_last) { float x[8]; ld8g(dh_last + row * H + j, x);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) dh[e] += x[e]; }
+                if (dc_last) { float x[8]; ld8g(dc_last + row * H + j, x);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) dc[sub * 8 + e] = x[e]; }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
+                const float tcv = ftanh(cc[e]);
+                const float dhe = dh[e] * keep;
+                const float d = (dc[sub * 8 + e] + dhe * go * (1.f - tcv * tcv)) * keep;
+                out[0][e] = d * gg_ * gi * (1.f - gi);
+                out[1][e] = d * cp[e] * gf * (1.f - gf);
+                out[2][e] = dhe * tcv * go * (1.f - go);
+                out[3][e] = d * gi * (1.f - gg_ * gg_);
+                dc[sub * 8 + e] = d * gf;
+              }
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) {
+                *reinterpret_cast<uint4*>(da16 + tr * 4 * H + gg * H + j) = ep_pack8(out[gg]);
+                st8g(da + tr * 4 * H + gg * H + j, out[gg]);
+              }
+            }
+          }
+        }
+        if (has_acc) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          atomicAdd(flag + (size_t)rb * T + t, 1);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static CUtensorMap ep_tmap_h(const __half* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   CUtensorMap tm;
@@ -340,6 +552,36 @@ void enc_pair_forward(LaunchCtx& cx, int T, int64_t R, int H, const __half* W1h1
   }
   k_enc_pair_fwd<<<p.groups * (p.nS1 + p.nS2), EP_THREADS, EP_SMEM, cx.stream>>>(tH1, tH2, tW1, tW2, p);
   check_launch(cx, "k_enc_pair_fwd");
+}
+
+
+// gates*/c* = the activations the forward saved; da*/da*_16 out (all T steps); flags int32 [2 * RB * T]
+void enc_pair_backward(LaunchCtx& cx, int T, int64_t R, int H, const __half* B1cat16, const __half* Whb2_16, const int32_t* mask,
+                       const float* gates1, const float* c1, const float* gates2, const float* c2, const float* dh_last1,
+                       const float* dc_last1, const float* dh_last2, const float* dc_last2, float* da1, __half* da1_16, float* da2,
+                       __half* da2_16, int* flags) {
+  using namespace tc;
+  VD_REQUIRE(enc_pair_shape_ok(R, H, cx.sm_count), VD_E_STATE, "enc_pair_backward: shape");
+  EncBwdParams p = {};
+  p.T = T; p.R = (int)R; p.H = H; p.RB = cdiv(R, 128);
+  p.nS1 = H / 16; p.nS2 = H / 32;
+  p.groups = std::max(1, std::min(p.RB, cx.sm_count / (p.nS1 + p.nS2)));
+  p.gates1 = gates1; p.c1 = c1; p.da1 = da1; p.da1_16 = da1_16;
+  p.gates2 = gates2; p.c2 = c2; p.da2 = da2; p.da2_16 = da2_16;
+  p.dh_last1 = dh_last1; p.dc_last1 = dc_last1; p.dh_last2 = dh_last2; p.dc_last2 = dc_last2;
+  p.mask = mask; p.flags = flags;
+  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)2 * p.RB * T * sizeof(int), cx.stream));
+  const int64_t TR = (int64_t)T * R;
+  const int64_t G = 4 * (int64_t)H;
+  CUtensorMap tA1 = ep_tmap_h(da1_16, TR, G, G, 128), tA2 = ep_tmap_h(da2_16, TR, G, G, 128);
+  CUtensorMap tW1 = ep_tmap_h(B1cat16, H, 2 * G, 2 * G, 16), tW2 = ep_tmap_h(Whb2_16, H, G, G, 32);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_enc_pair_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM));
+    attr_set = true;
+  }
+  k_enc_pair_bwd<<<p.groups * (p.nS1 + p.nS2), EP_THREADS, EP_SMEM, cx.stream>>>(tA1, tA2, tW1, tW2, p);
+  check_launch(cx, "k_enc_pair_bwd");
 }
 
 }  // namespace vd

@@ -698,6 +698,30 @@ void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2,
                                 const float* dc_last1, float* dx1_out, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) {
   const int H = l2.H, G = 4 * l2.H;
   const int64_t R = l2.R;
+  if (math_mode == VD_MATH_F16 && enc_persist_enabled() && l1.h16 && l2.h16 && l1.saved && l2.saved && l2.D == H && l1.T == l2.T &&
+      enc_pair_shape_ok(R, H, cx.sm_count)) {
+    // the forward of this pair ran as the persistent kernel: so does its BPTT (enc_lstm.cu::k_enc_pair_bwd) — one launch for
+    // both layers and all time steps; the weight / input gradients follow as batched contractions over all T*R rows
+    const int T = l2.T;
+    const int64_t TR = (int64_t)T * R;
+    cx.stream = sa;
+    l1.da = arena.get<float>(TR * G); l2.da = arena.get<float>(TR * G);
+    l1.da16 = arena.get<__half>(TR * G); l2.da16 = arena.get<__half>(TR * G);
+    __half* Whb2 = arena.get<__half>((int64_t)H * G);
+    __half* B1cat = arena.get<__half>((int64_t)H * 2 * G);
+    cvt_f32_to_f16(cx, Whb2, G, Wp(l2.wseg) + (int64_t)l2.D * G, G, H, G);                 // Wh2: rows D2.. of (D2+H, 4H)
+    cvt_f32_to_f16(cx, B1cat, 2 * G, Wp(l2.wseg), G, H, G);                                 // [Wx2 | ...]: rows 0..H-1 of layer 2
+    cvt_f32_to_f16(cx, B1cat + G, 2 * G, Wp(l1.wseg) + (int64_t)l1.D * G, G, H, G);         // [... | Wh1]
+    int* flags = arena.get<int>(2 * (int64_t)cdiv(R, 128) * T);
+    {
+      LaunchCtx::Scope sc2(&cx, "enc_pair_bwd", 2.0 * T * R * (double)H * 3.0 * G, 4.0 * T * R * (4.0 * G + 4.0 * H));
+      enc_pair_backward(cx, T, R, H, B1cat, Whb2, l1.mask, l1.gates, l1.c, l2.gates, l2.c, dh_last1, dc_last1, dh_last2, dc_last2,
+                        l1.da, l1.da16, l2.da, l2.da16, flags);
+    }
+    lstm_backward_end(l2, nullptr, nullptr, nullptr);
+    lstm_backward_end(l1, dx1_out, nullptr, nullptr);
+    return;
+  }
   float* dx2 = arena.get<float>((int64_t)l2.T * R * l2.D);      // = gradient wrt layer-1 outputs, all steps
   const bool pipelined = tcmode() && H % 128 == 0 && sb != nullptr && sb != sa && R >= wavefront_min_rows();
   const bool three = pipelined && sc != nullptr && sc != sa && sc != sb && three_streams_enabled();
@@ -992,11 +1016,15 @@ void Engine::encoder_backward(const float* dEnc) {
   // question LSTMs (+ gradients handed back by the gen decoder, gen.lua:45-60); the history chain's BPTT runs
   // concurrently on the side stream (disjoint weight segments; the shared embedding gradient is atomics-only)
   const bool embdrop = cfg.enc == ENC_MN_ATT;
+  // (persistent pair kernels must not be co-scheduled — see encoder_forward: in that mode both BPTTs run on the main stream)
+  const bool serial_pairs = math_mode == VD_MATH_F16 && enc_persist_enabled() && hist1.h16 != nullptr;
   if (cfg.useHist) {
-    fork_side();
+    if (serial_pairs) { join_side(); cx.stream = main_stream; } else fork_side();
+    cudaStream_t hs = serial_pairs ? main_stream : side_stream;
     float* dx1 = arena.get<float>(N * db.Th * E);
-    lstm_pair_backward(hist1, hist2, dh3, nullptr, nullptr, nullptr, dx1, side_stream, side2_stream, side3_stream);
-    reduce_segments(seg("hist.lstm1.weight"), seg("hist.lstm2.weight") + 1, side_stream);       // bucket 2
+    lstm_pair_backward(hist1, hist2, dh3, nullptr, nullptr, nullptr, dx1, hs, serial_pairs ? main2_stream : side2_stream,
+                       serial_pairs ? main3_stream : side3_stream);
+    reduce_segments(seg("hist.lstm1.weight"), seg("hist.lstm2.weight") + 1, hs);                // bucket 2
     embed_scatter_add(cx, dWp(0), dx1, E, ids_h, N * db.Th, E, embdrop ? d05 : dnone, SITE_HEMBED);
     back_to_main();
   }

@@ -171,4 +171,8 @@ bool enc_pair_shape_ok(int64_t R, int H, int sm_count);
 void enc_pair_forward(LaunchCtx& cx, int T, int64_t R, int H, const __half* W1h16, const __half* W2cat16, const float* bias2,
                       const int32_t* mask, float* gates1, float* c1, float* h1, __half* h1_16, float* gates2, float* c2, float* h2,
                       __half* h2_16, int* flags);
+void enc_pair_backward(LaunchCtx& cx, int T, int64_t R, int H, const __half* B1cat16, const __half* Whb2_16, const int32_t* mask,
+                       const float* gates1, const float* c1, const float* gates2, const float* c2, const float* dh_last1,
+                       const float* dc_last1, const float* dh_last2, const float* dc_last2, float* da1, __half* da1_16, float* da2,
+                       __half* da2_16, int* flags);
 }  // namespace vd
