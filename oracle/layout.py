@@ -46,23 +46,15 @@ def layout(p):
 
     add("wordEmbed.weight", V + 1, E, INIT_EMBED, 0)
     enc = p["encoder"]
-    if enc == "lf-ques":
-        lstm("ques.lstm1", E); lstm("ques.lstm2", H)
-        linear("fusion", H, H)
-    elif enc == "lf-ques-im-hist":
-        lstm("ques.lstm1", E); lstm("ques.lstm2", H)
-        lstm("hist.lstm1", E); lstm("hist.lstm2", H)
-        linear("fusion", H, 2 * H + F)
-    elif enc == "hrea-ques-im-hist":
-        linear("img.embed", IE, F)
-        lstm("hist.lstm1", E); lstm("hist.lstm2", H)
-        lstm("ques.lstm1", E + IE); lstm("ques.lstm2", H)
-        linear("att.q", 1, H); linear("att.h", 1, H)
-        lstm("dialog.lstm", 2 * H)
-    elif enc == "mn-att-ques-im-hist":
-        lstm("hist.lstm1", E); lstm("hist.lstm2", H)
-        lstm("ques.lstm1", E); lstm("ques.lstm2", H)
-        linear("mn.fact", H, H); linear("mn.query", H, H)
+    use_im, use_hist, att = "im" in enc, "hist" in enc, "att" in enc
+    known = ("lf-ques", "lf-ques-im", "lf-ques-hist", "lf-ques-im-hist", "lf-att-ques-im-hist", "hre-ques-hist", "hre-ques-im-hist",
+             "hrea-ques-im-hist", "mn-ques-hist", "mn-ques-im-hist", "mn-att-ques-im-hist")
+    if enc not in known:
+        raise ValueError("unknown encoder " + enc)
+    if enc == "lf-att-ques-im-hist":
+        hops = 1                     # hard-wired upstream (lf-att-ques-im-hist.lua:49)
+
+    def san():
         linear("san.img", H, F)
         for h in range(1, hops + 1):
             pre = "san.hop%d." % h
@@ -70,8 +62,32 @@ def layout(p):
             linear(pre + "ques_common", Cm, H)
             linear(pre + "score", 1, Cm)
         linear("san.out", H, H)
+
+    if enc.startswith("lf-") and not att:
+        lstm("ques.lstm1", E); lstm("ques.lstm2", H)
+        if use_hist:
+            lstm("hist.lstm1", E); lstm("hist.lstm2", H)
+        linear("fusion", H, H + (F if use_im else 0) + (H if use_hist else 0))
+    elif enc.startswith("hre"):
+        img_in_q = use_im
+        if img_in_q:
+            linear("img.embed", IE, F)
+        lstm("hist.lstm1", E); lstm("hist.lstm2", H)
+        lstm("ques.lstm1", E + (IE if img_in_q else 0)); lstm("ques.lstm2", H)
+        if enc.startswith("hrea"):
+            linear("att.q", 1, H); linear("att.h", 1, H)
+        lstm("dialog.lstm", 2 * H)
     else:
-        raise ValueError("unknown encoder " + enc)
+        lstm("hist.lstm1", E); lstm("hist.lstm2", H)
+        lstm("ques.lstm1", E); lstm("ques.lstm2", H)
+        if enc.startswith("lf-"):
+            linear("fusion", H, 2 * H)
+        if enc == "mn-ques-im-hist":
+            linear("mn.qi", H, H + F)
+        if enc.startswith("mn-"):
+            linear("mn.fact", H, H); linear("mn.query", H, H)
+        if att:
+            san()
     if p["decoder"] == "disc":
         lstm("opt.lstm", E)
     else:

@@ -332,7 +332,125 @@ def encoder_mn_att_ques_im_hist(ctx: Ctx, cfg, P, inputs):
     return out, {"rnnLayers": None}
 
 
+def encoder_lf_ques_im(ctx: Ctx, cfg, P, inputs):
+    """encoders/lf-ques-im.lua:3-43: JoinTable(2) [question | image] -> Dropout -> Linear(H+F,H) -> Tanh."""
+    x = lookup_table_mask_zero(P["wordEmbed.weight"], inputs["ques"])   # :15-16
+    l1, l2 = _two_layer_lstm(P, "ques", x)                              # :19-28
+    j = torch.cat([l2[0][-1], inputs["img"]], 1)                        # :31-35
+    j = dropout(ctx, j, cfg["dropout"], SITE_FUSION)                    # :36-38
+    out = torch.tanh(linear(j, P["fusion.weight"], P["fusion.bias"]))   # :39-40
+    return out, {"rnnLayers": [l1, l2]}
+
+
+def encoder_lf_ques_hist(ctx: Ctx, cfg, P, inputs):
+    """encoders/lf-ques-hist.lua:3-62: JoinTable(2) [question | history] -> Dropout -> Linear(2H,H) -> Tanh."""
+    x = lookup_table_mask_zero(P["wordEmbed.weight"], inputs["ques"])   # :15-16
+    l1, l2 = _two_layer_lstm(P, "ques", x)                              # :19-28
+    xh = lookup_table_mask_zero(P["wordEmbed.weight"], inputs["hist"])  # :31-36
+    _, h2 = _two_layer_lstm(P, "hist", xh)                              # :37-47
+    j = torch.cat([l2[0][-1], h2[0][-1]], 1)                            # :50-54
+    j = dropout(ctx, j, cfg["dropout"], SITE_FUSION)                    # :55-57
+    out = torch.tanh(linear(j, P["fusion.weight"], P["fusion.bias"]))   # :58-59
+    return out, {"rnnLayers": [l1, l2]}
+
+
+def _dialog_lstm(cfg, P, j):
+    """View(-1,10,2H) -> Transpose(1,2) -> SeqLSTM(2H,H) (no maskZero) -> Transpose(1,2) -> View(-1,H)
+    (hre-ques-hist.lua:63-68, hre-ques-im-hist.lua:90-94)."""
+    R, H = cfg["maxQuesCount"], cfg["rnnHiddenSize"]
+    j = j.view(-1, R, 2 * H).transpose(0, 1)
+    d, _ = seq_lstm(j, *lstm_p(P, "dialog.lstm"), maskzero=False)
+    return d.transpose(0, 1).reshape(-1, H)
+
+
+def encoder_hre_ques_hist(ctx: Ctx, cfg, P, inputs):
+    """encoders/hre-ques-hist.lua:3-71: [question | history] per round -> dialog-level SeqLSTM over the rounds."""
+    x = lookup_table_mask_zero(P["wordEmbed.weight"], inputs["ques"])   # :16-17
+    l1, l2 = _two_layer_lstm(P, "ques", x)                              # :20-29
+    xh = lookup_table_mask_zero(P["wordEmbed.weight"], inputs["hist"])  # :33-38
+    _, h2 = _two_layer_lstm(P, "hist", xh)                              # :39-50
+    j = torch.cat([l2[0][-1], h2[0][-1]], -1)                           # :59 JoinTable(1,1)
+    return _dialog_lstm(cfg, P, j), {"rnnLayers": [l1, l2]}             # :63-68
+
+
+def encoder_hre_ques_im_hist(ctx: Ctx, cfg, P, inputs):
+    """encoders/hre-ques-im-hist.lua:5-97: hrea-ques-im-hist without the history attention, and without the Dropout
+    in front of the image Linear (commented out upstream, :46)."""
+    ques, img, hist = inputs["ques"], inputs["img"], inputs["hist"]
+    W = lookup_table_mask_zero(P["wordEmbed.weight"], ques)             # :18-19
+    ie = linear(img, P["img.embed.weight"], P["img.embed.bias"])        # :43-48
+    I = mask_time(ques, ie)                                             # :50-53
+    xh = lookup_table_mask_zero(P["wordEmbed.weight"], hist)            # :23-28
+    _, h2 = _two_layer_lstm(P, "hist", xh)                              # :29-39
+    l1, l2 = _two_layer_lstm(P, "ques", torch.cat([W, I], -1))          # :65-79
+    j = torch.cat([l2[0][-1], h2[0][-1]], -1)                           # :82-86 JoinTable(-1)
+    return _dialog_lstm(cfg, P, j), {"rnnLayers": [l1, l2]}             # :90-94
+
+
+def _memory_block(ctx, cfg, P, q, h3, mask):
+    """MM(q, h^T) -> MaskSoftMax -> MM(probs, h) -> Dropout(0.5) -> Linear -> Tanh; + q; Linear -> Tanh
+    (mn-ques-hist.lua:46-63, mn-ques-im-hist.lua:51-68)."""
+    R, H = cfg["maxQuesCount"], cfg["rnnHiddenSize"]
+    qV, hV = q.view(-1, R, H), h3.view(-1, R, H)
+    qh = torch.bmm(qV, hV.transpose(1, 2))
+    probs = mask_softmax(qh.reshape(-1, R), mask).view(-1, R, R)
+    hAtt = torch.bmm(probs, hV).reshape(-1, H)
+    hAttTr = torch.tanh(linear(dropout(ctx, hAtt, 0.5, SITE_HATT), P["mn.fact.weight"], P["mn.fact.bias"]))
+    return torch.tanh(linear(hAttTr + q, P["mn.query.weight"], P["mn.query.bias"]))
+
+
+def _embdrop_lstms(ctx, P, inputs):
+    """Dropout(0.5) on both embedded sequences, two 2-layer maskZero LSTM stacks, last step of each
+    (mn-ques-hist.lua:22-43, mn-ques-im-hist.lua:24-45, lf-att-ques-im-hist.lua:20-41)."""
+    emb = P["wordEmbed.weight"]
+    qE = dropout(ctx, lookup_table_mask_zero(emb, inputs["ques"]), 0.5, SITE_QEMBED)
+    hE = dropout(ctx, lookup_table_mask_zero(emb, inputs["hist"]), 0.5, SITE_HEMBED)
+    _, h2 = _two_layer_lstm(P, "hist", hE)
+    _, q2 = _two_layer_lstm(P, "ques", qE)
+    return q2[0][-1], h2[0][-1]
+
+
+def encoder_mn_ques_hist(ctx: Ctx, cfg, P, inputs):
+    """encoders/mn-ques-hist.lua:5-71."""
+    q3, h3 = _embdrop_lstms(ctx, P, inputs)                             # :22-43
+    return _memory_block(ctx, cfg, P, q3, h3, inputs["mask"]), {"rnnLayers": None}   # :46-63
+
+
+def encoder_mn_ques_im_hist(ctx: Ctx, cfg, P, inputs):
+    """encoders/mn-ques-im-hist.lua:5-76: the memory query (and the residual) is Tanh(Linear(F+H,H)([q | fc7])), :47-48."""
+    q3, h3 = _embdrop_lstms(ctx, P, inputs)                             # :24-45
+    qi = torch.tanh(linear(torch.cat([q3, inputs["img"]], 1), P["mn.qi.weight"], P["mn.qi.bias"]))   # :47-48
+    return _memory_block(ctx, cfg, P, qi, h3, inputs["mask"]), {"rnnLayers": None}   # :51-68
+
+
+def encoder_lf_att_ques_im_hist(ctx: Ctx, cfg, P, inputs):
+    """encoders/lf-att-ques-im-hist.lua:3-93: qh = Tanh(Linear(2H,H)([q | h])) (:43), then ONE attention hop over pool5
+    (`num_attention_layer = 1` is hard-wired upstream, :49 — params.numAttentionLayers is not read) and the output layer."""
+    H, S2, C = cfg["rnnHiddenSize"], cfg["imgSpatialSize"] ** 2, cfg["imgFeatureSize"]
+    q3, h3 = _embdrop_lstms(ctx, P, inputs)                             # :20-41
+    u = torch.tanh(linear(torch.cat([q3, h3], 1), P["fusion.weight"], P["fusion.bias"]))   # :43
+    N = u.shape[0]
+    img_tr = torch.tanh(linear(inputs["img"].reshape(-1, C), P["san.img.weight"], P["san.img.bias"]))
+    img_tr = dropout(ctx, img_tr.view(N, S2, H), 0.5, SITE_IMG_TR)      # :52-56
+    pre = "san.hop1."
+    img_common = linear(img_tr.reshape(-1, H), P[pre + "img_common.weight"], P[pre + "img_common.bias"]).view(N, S2, -1)  # :61-63
+    ques_common = linear(u, P[pre + "ques_common.weight"], P[pre + "ques_common.bias"])    # :66
+    iq = dropout(ctx, torch.tanh(img_common + ques_common.unsqueeze(1)), 0.5, SITE_HOP0)   # :67-70
+    s = linear(iq.reshape(-1, iq.shape[-1]), P[pre + "score.weight"], P[pre + "score.bias"])   # :71
+    p = torch.softmax(s.view(N, S2), -1)                                # :72
+    u = torch.bmm(p.unsqueeze(1), img_tr).reshape(N, H) + u             # :75-80
+    out = torch.tanh(linear(dropout(ctx, u, 0.5, SITE_U_OUT), P["san.out.weight"], P["san.out.bias"]))   # :84
+    return out, {"rnnLayers": None}
+
+
 ENCODERS = {
+    "lf-ques-im": encoder_lf_ques_im,
+    "lf-ques-hist": encoder_lf_ques_hist,
+    "hre-ques-hist": encoder_hre_ques_hist,
+    "hre-ques-im-hist": encoder_hre_ques_im_hist,
+    "mn-ques-hist": encoder_mn_ques_hist,
+    "mn-ques-im-hist": encoder_mn_ques_im_hist,
+    "lf-att-ques-im-hist": encoder_lf_att_ques_im_hist,
     "lf-ques": encoder_lf_ques,
     "lf-ques-im-hist": encoder_lf_ques_im_hist,
     "hrea-ques-im-hist": encoder_hrea_ques_im_hist,

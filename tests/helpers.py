@@ -7,7 +7,14 @@ from visdial_b200.synthetic import make_batch
 
 CONFIGS = [("lf-ques", "gen"), ("lf-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen"),
            ("mn-att-ques-im-hist", "disc"), ("lf-ques", "disc"), ("mn-att-ques-im-hist", "gen"),
-           ("hrea-ques-im-hist", "disc"), ("lf-ques-im-hist", "gen")]
+           ("hrea-ques-im-hist", "disc"), ("lf-ques-im-hist", "gen"),
+           # the seven sub-graph encoders of encoders/*.lua (each once with either decoder; the ones that export
+           # rnnLayers to decoderConnect also with gen)
+           ("lf-ques-im", "disc"), ("lf-ques-im", "gen"), ("lf-ques-hist", "gen"), ("hre-ques-hist", "disc"),
+           ("hre-ques-hist", "gen"), ("hre-ques-im-hist", "gen"), ("mn-ques-hist", "gen"), ("mn-ques-im-hist", "disc"),
+           ("lf-att-ques-im-hist", "disc"), ("lf-att-ques-im-hist", "gen")]
+ALL_ENCODERS = ("lf-ques", "lf-ques-im", "lf-ques-hist", "lf-ques-im-hist", "lf-att-ques-im-hist", "hre-ques-hist",
+                "hre-ques-im-hist", "hrea-ques-im-hist", "mn-ques-hist", "mn-ques-im-hist", "mn-att-ques-im-hist")
 
 
 def small_params(encoder, decoder, **kw):

@@ -15,7 +15,8 @@ from visdial_b200.synthetic import make_corpus
 pytestmark = pytest.mark.gpu
 
 CONFIGS = [("lf-ques", "gen"), ("lf-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "disc"),
-           ("lf-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "gen")]
+           ("lf-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "gen"), ("lf-ques-im", "disc"), ("hre-ques-hist", "gen"),
+           ("mn-ques-im-hist", "disc"), ("lf-att-ques-im-hist", "disc")]
 
 
 def _opt(params, img_norm):
@@ -216,7 +217,8 @@ def test_model_retrieve_over_the_device_dataloader(enc, dec):
     d2.close(); model.engine.close()
 
 
-@pytest.mark.parametrize("enc", ["lf-ques", "hrea-ques-im-hist", "mn-att-ques-im-hist", "lf-ques-im-hist"])
+@pytest.mark.parametrize("enc", ["lf-ques", "hrea-ques-im-hist", "mn-att-ques-im-hist", "lf-ques-im-hist", "lf-ques-im", "hre-ques-im-hist",
+                                 "mn-ques-hist", "lf-att-ques-im-hist"])
 def test_generate_answers_matches_oracle(enc):
     """Model:generateAnswers (model.lua:432-613) — beam search and sampling driven through vd_gen_decoder_step on
     batches the device dataloader assembles — against oracle.generate_answers on the same dialog (fp32 math mode)."""

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helpers import full_params, small_batch, small_params
+from helpers import ALL_ENCODERS, full_params, small_batch, small_params
 from visdial_b200 import decoders, encoders
 from visdial_b200 import dist as vdist
 from visdial_b200.synthetic import make_batch
@@ -63,10 +63,13 @@ def test_batch_contract_headline_shapes():
 
 
 def test_plugin_loaders():
-    for name in ("lf-ques", "lf-ques-im-hist", "hrea-ques-im-hist", "mn-att-ques-im-hist"):
+    for name in ALL_ENCODERS:
         m = encoders.load(name)
         enc = m.model(small_params(name, "disc"))
-        assert (enc.rnnLayers is None) == name.startswith("mn")        # gModule encoders have no rnnLayers
+        # the gModule encoders (mn-*, lf-att-*) do not export rnnLayers (gen.lua:30 then skips decoderConnect's copy)
+        assert (enc.rnnLayers is None) == (name.startswith("mn") or name.startswith("lf-att"))
+    with pytest.raises(Exception):
+        encoders.load("lf-ques-im-hist-nope")
     for name in ("disc", "gen"):
         d = decoders.load(name)
         assert callable(d.model) and callable(d.forwardConnect) and callable(d.backwardConnect)
@@ -191,8 +194,7 @@ def test_oracle_layout_twin_matches_the_engine():
     from oracle import layout as OL
     from visdial_b200 import engine as E
     assert {k: bench.DEFAULTS[k] for k in E.DEFAULT_PARAMS} == E.DEFAULT_PARAMS
-    for enc, dec in [("lf-ques", "gen"), ("lf-ques-im-hist", "disc"), ("hrea-ques-im-hist", "gen"), ("mn-att-ques-im-hist", "disc"),
-                     ("mn-att-ques-im-hist", "gen")]:
+    for enc, dec in [(e, d) for e in ALL_ENCODERS for d in ("disc", "gen")]:
         p = small_params(enc, dec, numAttentionLayers=2 if "att" in enc else 1)
         segs, n = E.layout(p)
         osegs, on = OL.layout(p)

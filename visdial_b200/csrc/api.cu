@@ -226,7 +226,7 @@ int vd_encoder_rnn_state(vd_engine* h, int32_t level, const float** h_last, cons
     Engine* e = ENG(h);
     VD_REQUIRE(e->have_fwd, VD_E_STATE, "vd_encoder_rnn_state before vd_encoder_forward");
     VD_REQUIRE(level == 0 || level == 1, VD_E_BADARG, "level must be 0 or 1");
-    const bool has_layers = e->cfg.enc != vd::ENC_MN_ATT;            // the encoders that expose .rnnLayers (gen.lua:31)
+    const bool has_layers = e->cfg.rnn_layers;            // the encoders that expose .rnnLayers (gen.lua:31)
     const vd::LstmRun& r = level == 0 ? e->ques1 : e->ques2;
     if (h_last) *h_last = has_layers ? r.h_last() : nullptr;
     if (c_last) *c_last = has_layers ? r.c_last() : nullptr;

@@ -13,11 +13,14 @@ Cfg parse_cfg(const vd_params* p) {
   VD_REQUIRE(p && p->encoder && p->decoder, VD_E_BADARG, "params / encoder / decoder is null");
   Cfg c;
   c.encoder = p->encoder; c.decoder = p->decoder;
-  if (c.encoder == "lf-ques") c.enc = ENC_LF_QUES;
-  else if (c.encoder == "lf-ques-im-hist") c.enc = ENC_LF_QIH;
-  else if (c.encoder == "hrea-ques-im-hist") c.enc = ENC_HREA;
-  else if (c.encoder == "mn-att-ques-im-hist") c.enc = ENC_MN_ATT;
-  else VD_REQUIRE(false, VD_E_BADARG, "unknown encoder (lf-ques | lf-ques-im-hist | hrea-ques-im-hist | mn-att-ques-im-hist)");
+  struct { const char* name; int enc; } known[] = {
+      {"lf-ques", ENC_LF_QUES}, {"lf-ques-im-hist", ENC_LF_QIH}, {"hrea-ques-im-hist", ENC_HREA}, {"mn-att-ques-im-hist", ENC_MN_ATT},
+      {"lf-ques-im", ENC_LF_QI}, {"lf-ques-hist", ENC_LF_QH}, {"hre-ques-hist", ENC_HRE_QH}, {"hre-ques-im-hist", ENC_HRE_QIH},
+      {"mn-ques-hist", ENC_MN_QH}, {"mn-ques-im-hist", ENC_MN_QIH}, {"lf-att-ques-im-hist", ENC_LF_ATT}};
+  c.enc = -1;
+  for (auto& k : known)
+    if (c.encoder == k.name) c.enc = k.enc;
+  VD_REQUIRE(c.enc >= 0, VD_E_BADARG, "unknown encoder (one of the eleven names of encoders/*.lua)");
   if (c.decoder == "disc") c.dec = DEC_DISC;
   else if (c.decoder == "gen") c.dec = DEC_GEN;
   else VD_REQUIRE(false, VD_E_BADARG, "unknown decoder (disc | gen)");
@@ -28,6 +31,17 @@ Cfg parse_cfg(const vd_params* p) {
   c.useHist = c.encoder.find("hist") != std::string::npos;
   c.useIm = c.encoder.find("im") != std::string::npos;
   c.att = c.encoder.find("att") != std::string::npos;
+  c.fam_lf = c.encoder.compare(0, 3, "lf-") == 0;
+  c.fam_hre = c.encoder.compare(0, 3, "hre") == 0;
+  c.fam_mn = c.encoder.compare(0, 3, "mn-") == 0;
+  c.hre_att = c.enc == ENC_HREA;
+  c.san = c.att;
+  c.img_in_q = c.fam_hre && c.useIm;
+  c.img_drop = c.enc == ENC_HREA;
+  c.mn_qi = c.enc == ENC_MN_QIH;
+  c.embdrop = c.fam_mn || c.enc == ENC_LF_ATT;
+  c.rnn_layers = (c.fam_lf && !c.att) || c.fam_hre;
+  if (c.enc == ENC_LF_ATT) c.hops = 1;           // hard-wired upstream: lf-att-ques-im-hist.lua:49 does not read params.numAttentionLayers
   VD_REQUIRE(c.V > 2 && c.E > 0 && c.H > 0, VD_E_BADARG, "vocabSize / embedSize / rnnHiddenSize must be positive");
   VD_REQUIRE(c.L == 2, VD_E_BADARG, "numLayers must be 2");
   VD_REQUIRE(c.E % 4 == 0 && c.H % 32 == 0 && c.IE % 4 == 0 && c.Cm % 4 == 0 && c.F % 4 == 0, VD_E_BADARG,
@@ -60,36 +74,35 @@ static void add_linear(Layout& l, const std::string& n, int out, int in) {
 Layout build_layout(const Cfg& c) {
   Layout l;
   add_seg(l, "wordEmbed.weight", c.V + 1, c.E, VD_INIT_EMBED, 0);
-  switch (c.enc) {
-    case ENC_LF_QUES:
-      add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
-      add_linear(l, "fusion", c.H, c.H);
-      break;
-    case ENC_LF_QIH:
-      add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
-      add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
-      add_linear(l, "fusion", c.H, 2 * c.H + c.F);
-      break;
-    case ENC_HREA:
-      add_linear(l, "img.embed", c.IE, c.F);
-      add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
-      add_lstm(l, "ques.lstm1", c.E + c.IE, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
-      add_linear(l, "att.q", 1, c.H); add_linear(l, "att.h", 1, c.H);
-      add_lstm(l, "dialog.lstm", 2 * c.H, c.H);
-      break;
-    case ENC_MN_ATT:
-      add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
-      add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
-      add_linear(l, "mn.fact", c.H, c.H); add_linear(l, "mn.query", c.H, c.H);
-      add_linear(l, "san.img", c.H, c.F);
-      for (int h = 1; h <= c.hops; ++h) {
-        std::string p = "san.hop" + std::to_string(h) + ".";
-        add_linear(l, p + "img_common", c.Cm, c.H);
-        add_linear(l, p + "ques_common", c.Cm, c.H);
-        add_linear(l, p + "score", 1, c.Cm);
-      }
-      add_linear(l, "san.out", c.H, c.H);
-      break;
+  auto add_san = [&]() {
+    add_linear(l, "san.img", c.H, c.F);
+    for (int h = 1; h <= c.hops; ++h) {
+      std::string p = "san.hop" + std::to_string(h) + ".";
+      add_linear(l, p + "img_common", c.Cm, c.H);
+      add_linear(l, p + "ques_common", c.Cm, c.H);
+      add_linear(l, p + "score", 1, c.Cm);
+    }
+    add_linear(l, "san.out", c.H, c.H);
+  };
+  if (c.fam_lf && !c.san) {
+    // lf-ques / lf-ques-im / lf-ques-hist / lf-ques-im-hist: fusion over [q | img | h]
+    add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+    if (c.useHist) { add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H); }
+    add_linear(l, "fusion", c.H, c.H + (c.useIm ? c.F : 0) + (c.useHist ? c.H : 0));
+  } else if (c.fam_hre) {
+    if (c.img_in_q) add_linear(l, "img.embed", c.IE, c.F);
+    add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
+    add_lstm(l, "ques.lstm1", c.E + (c.img_in_q ? c.IE : 0), c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+    if (c.hre_att) { add_linear(l, "att.q", 1, c.H); add_linear(l, "att.h", 1, c.H); }
+    add_lstm(l, "dialog.lstm", 2 * c.H, c.H);
+  } else {
+    // mn-* and lf-att-ques-im-hist: history then question LSTMs, then the attention blocks
+    add_lstm(l, "hist.lstm1", c.E, c.H); add_lstm(l, "hist.lstm2", c.H, c.H);
+    add_lstm(l, "ques.lstm1", c.E, c.H); add_lstm(l, "ques.lstm2", c.H, c.H);
+    if (c.fam_lf) add_linear(l, "fusion", c.H, 2 * c.H);                   // lf-att: tanh(Linear([q | h]))
+    if (c.mn_qi) add_linear(l, "mn.qi", c.H, c.H + c.F);                   // mn-ques-im-hist: tanh(Linear([q | fc7]))
+    if (c.fam_mn) { add_linear(l, "mn.fact", c.H, c.H); add_linear(l, "mn.query", c.H, c.H); }
+    if (c.san) add_san();
   }
   if (c.dec == DEC_DISC) {
     add_lstm(l, "opt.lstm", c.E, c.H);
@@ -772,6 +785,107 @@ static LstmRun make_run(int T, int64_t R, int D, int H, int wseg, const float* x
   return r;
 }
 
+// ---- blocks shared by several encoder graphs -----------------------------------------------------------------------
+// memory network over the history facts (mn-*.lua): MM -> MaskSoftMax (causal) -> MM -> Dropout -> Linear -> Tanh, residual query, Linear -> Tanh
+void Engine::mn_block_fwd(const float* qin, const float* h3, float* out) {
+  const int H = cfg.H, R = cfg.R, B = db.B;
+  const int64_t N = db.N;
+  const DropCfg d05 = dropcfg(0.5f);
+  probs = arena.get<float>((int64_t)B * R * R);
+  hAtt = arena.get<float>(N * H);
+  mn_attention_fwd(cx, qin, h3, probs, hAtt, B, R, H);
+  hAtt_d = arena.get<float>(N * H);
+  dropout_apply(cx, hAtt_d, hAtt, N * H, d05, SITE_HATT);
+  hAttTr = arena.get<float>(N * H);
+  linear_fwd(seg("mn.fact.weight"), hAtt_d, N, hAttTr, 1);
+  sum1 = arena.get<float>(N * H);
+  add_out(cx, sum1, hAttTr, qin, N * H);
+  linear_fwd(seg("mn.query.weight"), sum1, N, out, 1);
+}
+// dout = gradient wrt `out` (post-tanh); dqin / dh3 receive the gradients wrt the query input and the facts
+void Engine::mn_block_bwd(const float* dout, const float* out, float* dqin, float* dh3) {
+  const int H = cfg.H, R = cfg.R, B = db.B;
+  const int64_t N = db.N;
+  const DropCfg d05 = dropcfg(0.5f);
+  float* dpre = arena.get<float>(N * H);
+  tanh_bwd(cx, dpre, dout, out, N * H);
+  float* dsum1 = arena.get<float>(N * H);
+  linear_bwd(seg("mn.query.weight"), sum1, dpre, N, dsum1, 0.f);
+  tanh_bwd(cx, dpre, dsum1, hAttTr, N * H);
+  float* dhAtt = arena.get<float>(N * H);
+  linear_bwd(seg("mn.fact.weight"), hAtt_d, dpre, N, dhAtt, 0.f);
+  dropout_apply(cx, dhAtt, dhAtt, N * H, d05, SITE_HATT);
+  mn_attention_bwd(cx, mn_query_in, hist2.h_last(), probs, dhAtt, dqin, dh3, B, R, H);
+  add_inplace(cx, dqin, dsum1, N * H);
+}
+// SAN (mn-att-ques-im-hist.lua:67-106, lf-att-ques-im-hist.lua:43-86): tanh(Linear(img)) is computed once per dialog; Dropout then
+// acts on the repeated tensor; hops of {img_common + ques_common -> tanh -> dropout -> score -> softmax -> weighted sum + u}
+void Engine::san_block_fwd(const float* u0) {
+  const int H = cfg.H, R = cfg.R, B = db.B;
+  const int64_t N = db.N;
+  const int P = cfg.S * cfg.S, Cm = cfg.Cm;
+  const DropCfg d05 = dropcfg(0.5f);
+  t_img = arena.get<float>((int64_t)B * P * H);
+  wait_img();
+  linear_fwd(seg("san.img.weight"), db.img, (int64_t)B * P, t_img, 1);
+  img_tr = arena.get<float>(N * P * H);
+  san_expand_dropout(cx, img_tr, t_img, B, R, P, H, d05, SITE_IMG_TR);
+  img_common.assign(cfg.hops, nullptr); ques_common.assign(cfg.hops, nullptr);
+  sc.assign(cfg.hops, nullptr); pr.assign(cfg.hops, nullptr); u_hop.assign(cfg.hops + 1, nullptr);
+  u_hop[0] = const_cast<float*>(u0);
+  for (int hop = 0; hop < cfg.hops; ++hop) {
+    std::string pre = "san.hop" + std::to_string(hop + 1) + ".";
+    int w_ic = seg((pre + "img_common.weight").c_str()), w_qc = seg((pre + "ques_common.weight").c_str()),
+        w_s = seg((pre + "score.weight").c_str());
+    img_common[hop] = arena.get<float>(N * P * Cm);
+    linear_fwd(w_ic, img_tr, N * P, img_common[hop], 0);
+    ques_common[hop] = arena.get<float>(N * Cm);
+    linear_fwd(w_qc, u_hop[hop], N, ques_common[hop], 0);
+    sc[hop] = arena.get<float>(N * P);
+    san_score_fwd(cx, img_common[hop], ques_common[hop], Wp(w_s), Wp(w_s + 1), sc[hop], N, P, Cm, d05, SITE_HOP0 + hop);
+    pr[hop] = arena.get<float>(N * P);
+    u_hop[hop + 1] = arena.get<float>(N * H);
+    san_softmax_att_fwd(cx, sc[hop], pr[hop], img_tr, u_hop[hop], u_hop[hop + 1], N, P, H);
+  }
+  u_d = arena.get<float>(N * H);
+  dropout_apply(cx, u_d, u_hop[cfg.hops], N * H, d05, SITE_U_OUT);
+  linear_fwd(seg("san.out.weight"), u_d, N, encOut, 1);
+}
+void Engine::san_block_bwd(const float* dEnc, float* du) {
+  const int H = cfg.H, R = cfg.R, B = db.B;
+  const int64_t N = db.N;
+  const int P = cfg.S * cfg.S, Cm = cfg.Cm;
+  const DropCfg d05 = dropcfg(0.5f);
+  float* dpre = arena.get<float>(N * H);
+  tanh_bwd(cx, dpre, dEnc, encOut, N * H);
+  linear_bwd(seg("san.out.weight"), u_d, dpre, N, du, 0.f);
+  dropout_apply(cx, du, du, N * H, d05, SITE_U_OUT);
+  float* dimg_tr = arena.get<float>(N * P * H);
+  float* ds = arena.get<float>(N * P);
+  float* dic = arena.get<float>(N * P * Cm);
+  float* dqc = arena.get<float>(N * Cm);
+  for (int hop = cfg.hops - 1; hop >= 0; --hop) {
+    std::string pre = "san.hop" + std::to_string(hop + 1) + ".";
+    int w_ic = seg((pre + "img_common.weight").c_str()), w_qc = seg((pre + "ques_common.weight").c_str()),
+        w_s = seg((pre + "score.weight").c_str());
+    if (hop == cfg.hops - 1) {
+      san_att_bwd(cx, du, pr[hop], img_tr, ds, dimg_tr, N, P, H);
+    } else {
+      float* tmp = arena.get<float>(N * P * H);
+      san_att_bwd(cx, du, pr[hop], img_tr, ds, tmp, N, P, H);
+      add_inplace(cx, dimg_tr, tmp, N * P * H);
+    }
+    san_score_bwd(cx, ds, img_common[hop], ques_common[hop], Wp(w_s), dic, dqc, dWp(w_s), dWp(w_s + 1), N, P, Cm, d05,
+                  SITE_HOP0 + hop);
+    linear_bwd(w_ic, img_tr, dic, N * P, dimg_tr, 1.f);
+    linear_bwd(w_qc, u_hop[hop], dqc, N, du, 1.f);          // du now = grad wrt u_hop[hop]
+  }
+  float* dt_pre = arena.get<float>((int64_t)B * P * H);
+  san_collapse_bwd(cx, dimg_tr, t_img, dt_pre, B, R, P, H, d05, SITE_IMG_TR);
+  linear_bwd(seg("san.img.weight"), db.img, dt_pre, (int64_t)B * P, nullptr, 0.f);
+  release_img();                                   // last reader of this step's image staging buffer
+}
+
 void Engine::encoder_forward(const vd_batch* b) {
   VD_CUDA_CHECK(cudaSetDevice(cfg.gpuid));
   if (side_active) { cudaStreamSynchronize(side_stream); side_active = false; }   // only after an aborted call
@@ -799,7 +913,7 @@ void Engine::encoder_forward(const vd_batch* b) {
     ids_h = arena.get<int32_t>(N * db.Th);
     transpose_ids(cx, db.hist, ids_h, N, db.Th);
   }
-  const bool embdrop = cfg.enc == ENC_MN_ATT;              // mn-att-ques-im-hist.lua:24-25
+  const bool embdrop = cfg.embdrop;                        // mn-*.lua / lf-att-*.lua: Dropout(0.5) on both embeddings
   // history branch
   if (cfg.useHist) {
     fork_side();
@@ -822,12 +936,12 @@ void Engine::encoder_forward(const vd_batch* b) {
   // question branch
   xq = arena.get<float>(N * db.Tq * E);
   embed_rows(cx, xq, Wp(0), ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
-  if (cfg.enc == ENC_HREA) {
-    // hrea-ques-im-hist.lua:45-55: Dropout(0.5) -> Linear(F,IE) on the 10x repeated fc7, MaskTime, JoinTable(-1)
+  if (cfg.img_in_q) {
+    // hre(a)-ques-im-hist.lua:41-55: [Dropout(0.5) ->] Linear(F,IE) on the 10x repeated fc7, MaskTime, JoinTable(-1)
     img_d = arena.get<float>(N * cfg.F);
     wait_img();
     repeat_rows(cx, img_d, db.img, B, R, cfg.F);
-    dropout_apply(cx, img_d, img_d, N * cfg.F, d05, SITE_IMG_FC7);
+    if (cfg.img_drop) dropout_apply(cx, img_d, img_d, N * cfg.F, d05, SITE_IMG_FC7);
     img_e = arena.get<float>(N * cfg.IE);
     linear_fwd(seg("img.embed.weight"), img_d, N, img_e, 0);
     qi_in = arena.get<float>(N * db.Tq * (E + cfg.IE));
@@ -843,36 +957,47 @@ void Engine::encoder_forward(const vd_batch* b) {
   const float* h3 = cfg.useHist ? hist2.h_last() : nullptr;
   encOut = arena.get<float>(N * H);
 
-  if (cfg.enc == ENC_LF_QUES || cfg.enc == ENC_LF_QIH) {
-    // lf-ques.lua:29-33 / lf-ques-im-hist.lua:49-59
-    joinK = cfg.enc == ENC_LF_QUES ? H : 2 * H + cfg.F;
+  if (cfg.fam_lf) {
+    // lf-ques.lua:29-33 / lf-ques-im.lua / lf-ques-hist.lua / lf-ques-im-hist.lua:49-59: JoinTable [q | img | h] -> Dropout -> Linear
+    // -> Tanh.  lf-att-ques-im-hist.lua:41: Tanh(Linear([q | h])) with no dropout, then the SAN block on pool5.
+    const bool fc7 = cfg.useIm && !cfg.san;
+    joinK = H + (fc7 ? cfg.F : 0) + (cfg.useHist ? H : 0);
     join_d = arena.get<float>(N * joinK);
     copy_cols(cx, join_d, joinK, q3, H, N, H);
-    if (cfg.enc == ENC_LF_QIH) {
-      // image repeated per round (model.lua:267-269), concat order [q | img | h]
+    if (fc7) {                                          // image repeated per round (model.lua:267-269)
       float* tmp = arena.get<float>(N * cfg.F);
       wait_img();
       repeat_rows(cx, tmp, db.img, B, R, cfg.F);
       copy_cols(cx, join_d + H, joinK, tmp, cfg.F, N, cfg.F);
-      copy_cols(cx, join_d + H + cfg.F, joinK, h3, H, N, H);
     }
-    dropout_apply(cx, join_d, join_d, N * joinK, dp, SITE_FUSION);
-    linear_fwd(seg("fusion.weight"), join_d, N, encOut, 1);
-  } else if (cfg.enc == ENC_HREA) {
-    // hrea-ques-im-hist.lua:89-137
-    sq = arena.get<float>(N); sh = arena.get<float>(N);
-    int sq_w = seg("att.q.weight"), sh_w = seg("att.h.weight");
-    rowdot_fwd(cx, sq, q3, Wp(sq_w), Wp(sq_w + 1), N, H);
-    rowdot_fwd(cx, sh, h3, Wp(sh_w), Wp(sh_w + 1), N, H);
-    probs = arena.get<float>((int64_t)B * R * R);
-    att = arena.get<float>(N * H);
-    hrea_attention_fwd(cx, sq, sh, h3, probs, att, B, R, H);
-    // JoinTable(-1) [att | Qi], View(-1,10,2H), Transpose(1,2): row (r,b) <- row (b,r)
+    if (cfg.useHist) copy_cols(cx, join_d + H + (fc7 ? cfg.F : 0), joinK, h3, H, N, H);
+    if (!cfg.san) {
+      dropout_apply(cx, join_d, join_d, N * joinK, dp, SITE_FUSION);
+      linear_fwd(seg("fusion.weight"), join_d, N, encOut, 1);
+    } else {
+      qh2 = arena.get<float>(N * H);
+      linear_fwd(seg("fusion.weight"), join_d, N, qh2, 1);
+      san_block_fwd(qh2);
+    }
+  } else if (cfg.fam_hre) {
+    // hrea-ques-im-hist.lua:89-137 (attention over the rounds, [att | q]) / hre-ques-*.lua ([q | h]) -> dialog-level LSTM
     jt = arena.get<float>(N * 2 * H);
     float* j = arena.get<float>(N * 2 * H);
-    copy_cols(cx, j, 2 * H, att, H, N, H);
-    copy_cols(cx, j + H, 2 * H, q3, H, N, H);
-    // permute rows (b,r) -> (r,b) with a strided 2-D copy per round
+    if (cfg.hre_att) {
+      sq = arena.get<float>(N); sh = arena.get<float>(N);
+      int sq_w = seg("att.q.weight"), sh_w = seg("att.h.weight");
+      rowdot_fwd(cx, sq, q3, Wp(sq_w), Wp(sq_w + 1), N, H);
+      rowdot_fwd(cx, sh, h3, Wp(sh_w), Wp(sh_w + 1), N, H);
+      probs = arena.get<float>((int64_t)B * R * R);
+      att = arena.get<float>(N * H);
+      hrea_attention_fwd(cx, sq, sh, h3, probs, att, B, R, H);
+      copy_cols(cx, j, 2 * H, att, H, N, H);
+      copy_cols(cx, j + H, 2 * H, q3, H, N, H);
+    } else {
+      copy_cols(cx, j, 2 * H, q3, H, N, H);
+      copy_cols(cx, j + H, 2 * H, h3, H, N, H);
+    }
+    // View(-1,10,2H), Transpose(1,2): row (r,b) <- row (b,r), a strided 2-D copy per round
     for (int rr = 0; rr < R; ++rr)
       copy_cols(cx, jt + (int64_t)rr * B * 2 * H, 2 * H, j + (int64_t)rr * 2 * H, (int64_t)R * 2 * H, B, 2 * H);
     dialog = make_run(R, B, 2 * H, H, seg("dialog.lstm.weight"), jt, nullptr, nullptr);
@@ -880,45 +1005,26 @@ void Engine::encoder_forward(const vd_batch* b) {
     for (int rr = 0; rr < R; ++rr)
       copy_cols(cx, encOut + (int64_t)rr * H, (int64_t)R * H, dialog.h + (int64_t)rr * B * H, H, B, H);
   } else {
-    // mn-att-ques-im-hist.lua:48-106
-    const int P = cfg.S * cfg.S, Cm = cfg.Cm;
-    probs = arena.get<float>((int64_t)B * R * R);
-    hAtt = arena.get<float>(N * H);
-    mn_attention_fwd(cx, q3, h3, probs, hAtt, B, R, H);
-    hAtt_d = arena.get<float>(N * H);
-    dropout_apply(cx, hAtt_d, hAtt, N * H, d05, SITE_HATT);
-    hAttTr = arena.get<float>(N * H);
-    linear_fwd(seg("mn.fact.weight"), hAtt_d, N, hAttTr, 1);
-    sum1 = arena.get<float>(N * H);
-    add_out(cx, sum1, hAttTr, q3, N * H);
-    qh2 = arena.get<float>(N * H);
-    linear_fwd(seg("mn.query.weight"), sum1, N, qh2, 1);
-    // SAN: tanh(Linear(img)) is computed once per dialog; Dropout then acts on the repeated tensor (:74-78)
-    t_img = arena.get<float>((int64_t)B * P * H);
-    wait_img();
-    linear_fwd(seg("san.img.weight"), db.img, (int64_t)B * P, t_img, 1);
-    img_tr = arena.get<float>(N * P * H);
-    san_expand_dropout(cx, img_tr, t_img, B, R, P, H, d05, SITE_IMG_TR);
-    img_common.assign(cfg.hops, nullptr); ques_common.assign(cfg.hops, nullptr);
-    sc.assign(cfg.hops, nullptr); pr.assign(cfg.hops, nullptr); u_hop.assign(cfg.hops + 1, nullptr);
-    u_hop[0] = qh2;
-    for (int hop = 0; hop < cfg.hops; ++hop) {
-      std::string pre = "san.hop" + std::to_string(hop + 1) + ".";
-      int w_ic = seg((pre + "img_common.weight").c_str()), w_qc = seg((pre + "ques_common.weight").c_str()),
-          w_s = seg((pre + "score.weight").c_str());
-      img_common[hop] = arena.get<float>(N * P * Cm);
-      linear_fwd(w_ic, img_tr, N * P, img_common[hop], 0);
-      ques_common[hop] = arena.get<float>(N * Cm);
-      linear_fwd(w_qc, u_hop[hop], N, ques_common[hop], 0);
-      sc[hop] = arena.get<float>(N * P);
-      san_score_fwd(cx, img_common[hop], ques_common[hop], Wp(w_s), Wp(w_s + 1), sc[hop], N, P, Cm, d05, SITE_HOP0 + hop);
-      pr[hop] = arena.get<float>(N * P);
-      u_hop[hop + 1] = arena.get<float>(N * H);
-      san_softmax_att_fwd(cx, sc[hop], pr[hop], img_tr, u_hop[hop], u_hop[hop + 1], N, P, H);
+    // mn-ques-hist.lua / mn-ques-im-hist.lua / mn-att-ques-im-hist.lua:48-106
+    mn_query_in = q3;
+    if (cfg.mn_qi) {                                    // mn-ques-im-hist.lua: qi_proj = Tanh(Linear([q | fc7]))
+      qi_join = arena.get<float>(N * (H + cfg.F));
+      copy_cols(cx, qi_join, H + cfg.F, q3, H, N, H);
+      float* tmp = arena.get<float>(N * cfg.F);
+      wait_img();
+      repeat_rows(cx, tmp, db.img, B, R, cfg.F);
+      copy_cols(cx, qi_join + H, H + cfg.F, tmp, cfg.F, N, cfg.F);
+      qi_proj = arena.get<float>(N * H);
+      linear_fwd(seg("mn.qi.weight"), qi_join, N, qi_proj, 1);
+      mn_query_in = qi_proj;
     }
-    u_d = arena.get<float>(N * H);
-    dropout_apply(cx, u_d, u_hop[cfg.hops], N * H, d05, SITE_U_OUT);
-    linear_fwd(seg("san.out.weight"), u_d, N, encOut, 1);
+    if (cfg.san) {
+      qh2 = arena.get<float>(N * H);
+      mn_block_fwd(mn_query_in, h3, qh2);
+      san_block_fwd(qh2);
+    } else {
+      mn_block_fwd(mn_query_in, h3, encOut);
+    }
   }
   wait_img();                // (an encoder that never reads the image still has to retire the copy before the buffer is reused)
   release_img();             // forward-only callers never reach the backward's release; a later one simply overrides this
@@ -940,14 +1046,22 @@ void Engine::encoder_backward(const float* dEnc) {
   if (cfg.dec == DEC_GEN) reduce_segments(seg("dec.lstm1.weight"), (int)lay.segs.size() - 1, main_stream);
   else if (!opt_bwd_pending) reduce_segments(seg("opt.lstm.weight"), (int)lay.segs.size() - 1, main_stream);
 
-  if (cfg.enc == ENC_LF_QUES || cfg.enc == ENC_LF_QIH) {
-    tanh_bwd(cx, dpre, dEnc, encOut, N * H);
+  if (cfg.fam_lf) {
+    const bool fc7 = cfg.useIm && !cfg.san;
     float* dj = arena.get<float>(N * joinK);
-    linear_bwd(seg("fusion.weight"), join_d, dpre, N, dj, 0.f);
-    dropout_apply(cx, dj, dj, N * joinK, dp, SITE_FUSION);
+    if (!cfg.san) {
+      tanh_bwd(cx, dpre, dEnc, encOut, N * H);
+      linear_bwd(seg("fusion.weight"), join_d, dpre, N, dj, 0.f);
+      dropout_apply(cx, dj, dj, N * joinK, dp, SITE_FUSION);
+    } else {
+      float* dqh = arena.get<float>(N * H);
+      san_block_bwd(dEnc, dqh);
+      tanh_bwd(cx, dpre, dqh, qh2, N * H);
+      linear_bwd(seg("fusion.weight"), join_d, dpre, N, dj, 0.f);
+    }
     copy_cols(cx, dq3, H, dj, joinK, N, H);
-    if (cfg.enc == ENC_LF_QIH) copy_cols(cx, dh3, H, dj + H + cfg.F, joinK, N, H);
-  } else if (cfg.enc == ENC_HREA) {
+    if (cfg.useHist) copy_cols(cx, dh3, H, dj + H + (fc7 ? cfg.F : 0), joinK, N, H);
+  } else if (cfg.fam_hre) {
     const float* q3 = ques2.h_last();
     const float* h3 = hist2.h_last();
     // un-permute the gradient (n = b*R + r) -> (r,b), BPTT over rounds
@@ -959,63 +1073,42 @@ void Engine::encoder_backward(const float* dEnc) {
     float* dj = arena.get<float>(N * 2 * H);
     for (int rr = 0; rr < R; ++rr)
       copy_cols(cx, dj + (int64_t)rr * 2 * H, (int64_t)R * 2 * H, djt + (int64_t)rr * B * 2 * H, 2 * H, B, 2 * H);
-    float* datt = arena.get<float>(N * H);
-    copy_cols(cx, datt, H, dj, 2 * H, N, H);
-    copy_cols(cx, dq3, H, dj + H, 2 * H, N, H);
-    float* dsq = arena.get<float>(N); float* dsh = arena.get<float>(N);
-    hrea_attention_bwd(cx, sq, sh, h3, probs, datt, dsq, dsh, dh3, B, R, H);
-    int sq_w = seg("att.q.weight"), sh_w = seg("att.h.weight");
-    rowdot_bwd(cx, dsq, q3, Wp(sq_w), dq3, 1, dWp(sq_w), dWp(sq_w + 1), N, H);
-    rowdot_bwd(cx, dsh, h3, Wp(sh_w), dh3, 1, dWp(sh_w), dWp(sh_w + 1), N, H);
-  } else {
-    const int P = cfg.S * cfg.S, Cm = cfg.Cm;
-    const float* q3 = ques2.h_last();
-    const float* h3 = hist2.h_last();
-    tanh_bwd(cx, dpre, dEnc, encOut, N * H);
-    float* du = arena.get<float>(N * H);
-    linear_bwd(seg("san.out.weight"), u_d, dpre, N, du, 0.f);
-    dropout_apply(cx, du, du, N * H, d05, SITE_U_OUT);
-    float* dimg_tr = arena.get<float>(N * P * H);
-    float* ds = arena.get<float>(N * P);
-    float* dic = arena.get<float>(N * P * Cm);
-    float* dqc = arena.get<float>(N * Cm);
-    for (int hop = cfg.hops - 1; hop >= 0; --hop) {
-      std::string pre = "san.hop" + std::to_string(hop + 1) + ".";
-      int w_ic = seg((pre + "img_common.weight").c_str()), w_qc = seg((pre + "ques_common.weight").c_str()),
-          w_s = seg((pre + "score.weight").c_str());
-      if (hop == cfg.hops - 1) {
-        san_att_bwd(cx, du, pr[hop], img_tr, ds, dimg_tr, N, P, H);
-      } else {
-        float* tmp = arena.get<float>(N * P * H);
-        san_att_bwd(cx, du, pr[hop], img_tr, ds, tmp, N, P, H);
-        add_inplace(cx, dimg_tr, tmp, N * P * H);
-      }
-      san_score_bwd(cx, ds, img_common[hop], ques_common[hop], Wp(w_s), dic, dqc, dWp(w_s), dWp(w_s + 1), N, P, Cm, d05,
-                    SITE_HOP0 + hop);
-      linear_bwd(w_ic, img_tr, dic, N * P, dimg_tr, 1.f);
-      linear_bwd(w_qc, u_hop[hop], dqc, N, du, 1.f);          // du now = grad wrt u_hop[hop]
+    if (cfg.hre_att) {
+      float* datt = arena.get<float>(N * H);
+      copy_cols(cx, datt, H, dj, 2 * H, N, H);
+      copy_cols(cx, dq3, H, dj + H, 2 * H, N, H);
+      float* dsq = arena.get<float>(N); float* dsh = arena.get<float>(N);
+      hrea_attention_bwd(cx, sq, sh, h3, probs, datt, dsq, dsh, dh3, B, R, H);
+      int sq_w = seg("att.q.weight"), sh_w = seg("att.h.weight");
+      rowdot_bwd(cx, dsq, q3, Wp(sq_w), dq3, 1, dWp(sq_w), dWp(sq_w + 1), N, H);
+      rowdot_bwd(cx, dsh, h3, Wp(sh_w), dh3, 1, dWp(sh_w), dWp(sh_w + 1), N, H);
+    } else {
+      copy_cols(cx, dq3, H, dj, 2 * H, N, H);
+      copy_cols(cx, dh3, H, dj + H, 2 * H, N, H);
     }
-    float* dt_pre = arena.get<float>((int64_t)B * P * H);
-    san_collapse_bwd(cx, dimg_tr, t_img, dt_pre, B, R, P, H, d05, SITE_IMG_TR);
-    linear_bwd(seg("san.img.weight"), db.img, dt_pre, (int64_t)B * P, nullptr, 0.f);
-    release_img();                                   // last reader of this step's image staging buffer
-    // memory network part, :48-65
-    tanh_bwd(cx, dpre, du, qh2, N * H);
-    float* dsum1 = arena.get<float>(N * H);
-    linear_bwd(seg("mn.query.weight"), sum1, dpre, N, dsum1, 0.f);
-    tanh_bwd(cx, dpre, dsum1, hAttTr, N * H);
-    float* dhAtt = arena.get<float>(N * H);
-    linear_bwd(seg("mn.fact.weight"), hAtt_d, dpre, N, dhAtt, 0.f);
-    dropout_apply(cx, dhAtt, dhAtt, N * H, d05, SITE_HATT);
-    mn_attention_bwd(cx, q3, h3, probs, dhAtt, dq3, dh3, B, R, H);
-    add_inplace(cx, dq3, dsum1, N * H);
-    // bucket 1: every non-recurrent layer of the encoder (mn.*, san.*) is final here, before the LSTM BPTTs start
-    reduce_segments(seg("mn.fact.weight"), seg("san.out.weight") + 1, main_stream);
+  } else {
+    // memory-network family: [SAN ->] memory block -> [qi projection]
+    float* dqin = cfg.mn_qi ? arena.get<float>(N * H) : dq3;
+    if (cfg.san) {
+      float* du = arena.get<float>(N * H);
+      san_block_bwd(dEnc, du);
+      mn_block_bwd(du, qh2, dqin, dh3);
+    } else {
+      mn_block_bwd(dEnc, encOut, dqin, dh3);
+    }
+    if (cfg.mn_qi) {
+      tanh_bwd(cx, dpre, dqin, qi_proj, N * H);
+      float* dqj = arena.get<float>(N * (H + cfg.F));
+      linear_bwd(seg("mn.qi.weight"), qi_join, dpre, N, dqj, 0.f);
+      copy_cols(cx, dq3, H, dqj, H + cfg.F, N, H);
+    }
+    // gradient sync, bucket 1: every non-recurrent layer of the encoder is final here, before the LSTM BPTTs start
+    if (cfg.san) reduce_segments(seg(cfg.mn_qi ? "mn.qi.weight" : "mn.fact.weight"), seg("san.out.weight") + 1, main_stream);
   }
 
   // question LSTMs (+ gradients handed back by the gen decoder, gen.lua:45-60); the history chain's BPTT runs
   // concurrently on the side stream (disjoint weight segments; the shared embedding gradient is atomics-only)
-  const bool embdrop = cfg.enc == ENC_MN_ATT;
+  const bool embdrop = cfg.embdrop;
   // (persistent pair kernels must not be co-scheduled — see encoder_forward: in that mode both BPTTs run on the main stream)
   const bool serial_pairs = math_mode == VD_MATH_F16 && enc_persist_enabled() && hist1.h16 != nullptr;
   if (cfg.useHist) {
@@ -1034,7 +1127,7 @@ void Engine::encoder_backward(const float* dEnc) {
     lstm_pair_backward(ques1, ques2, dq3, conn_dc_l2, conn_dh_l1, conn_dc_l1, dx1, main_stream, main2_stream, main3_stream);
     reduce_segments(seg("ques.lstm1.weight"), seg("ques.lstm2.weight") + 1, main_stream);       // bucket 3
     embed_scatter_add(cx, dWp(0), dx1, D1, ids_q, N * db.Tq, E, embdrop ? d05 : dnone, SITE_QEMBED);
-    if (cfg.enc == ENC_HREA) {
+    if (cfg.img_in_q) {
       float* die = arena.get<float>(N * cfg.IE);
       masktime_bwd(cx, dx1, D1, E, ids_q, die, db.Tq, N, cfg.IE);
       linear_bwd(seg("img.embed.weight"), img_d, die, N, nullptr, 0.f);
@@ -1073,7 +1166,7 @@ void Engine::forward_connect() {
   if (cfg.dec != DEC_GEN) return;
   VD_REQUIRE(have_fwd, VD_E_STATE, "forward_connect before encoder_forward");
   gen_h0[0] = gen_h0[1] = gen_c0[0] = gen_c0[1] = nullptr;
-  if (cfg.enc != ENC_MN_ATT) {                       // encoders with .rnnLayers
+  if (cfg.rnn_layers) {                              // encoders with .rnnLayers
     gen_h0[0] = ques1.h_last(); gen_c0[0] = ques1.c_last();
     gen_c0[1] = ques2.c_last();
   }
@@ -1268,7 +1361,7 @@ const float* Engine::backward_connect() {
   // decoders/gen.lua:45-60
   if (cfg.dec == DEC_DISC) return dEncFromDec;     // t[2] of model.lua:335
   conn_dh_l1 = conn_dc_l1 = conn_dc_l2 = nullptr;
-  if (cfg.enc != ENC_MN_ATT) {
+  if (cfg.rnn_layers) {
     conn_dc_l1 = gen_dc0[0]; conn_dc_l2 = gen_dc0[1];
     conn_dh_l1 = gen_dh0[0];
   }

@@ -8,7 +8,8 @@
 
 namespace vd {
 
-enum EncKind { ENC_LF_QUES = 0, ENC_LF_QIH = 1, ENC_HREA = 2, ENC_MN_ATT = 3 };
+enum EncKind { ENC_LF_QUES = 0, ENC_LF_QIH = 1, ENC_HREA = 2, ENC_MN_ATT = 3, ENC_LF_QI = 4, ENC_LF_QH = 5, ENC_HRE_QH = 6, ENC_HRE_QIH = 7,
+               ENC_MN_QH = 8, ENC_MN_QIH = 9, ENC_LF_ATT = 10 };
 enum DecKind { DEC_DISC = 0, DEC_GEN = 1 };
 
 struct Cfg {
@@ -18,6 +19,15 @@ struct Cfg {
   float dropout = 0.5f;
   int gpuid = 0;
   bool useIm = false, useHist = false, att = false;
+  // structure of the encoder graph, derived from its name (encoders/*.lua): late fusion / hierarchical / memory network
+  bool fam_lf = false, fam_hre = false, fam_mn = false;
+  bool hre_att = false;     // hrea: attention over the history rounds before the dialog LSTM
+  bool san = false;         // SAN spatial attention over pool5 (mn-att-*, lf-att-*)
+  bool img_in_q = false;    // Linear(fc7) -> MaskTime -> concatenated to the question LSTM input (hre-ques-im-hist, hrea-*)
+  bool img_drop = false;    // ... behind Dropout(0.5) (hrea only; commented out in hre-ques-im-hist.lua:45)
+  bool mn_qi = false;       // mn-ques-im-hist: tanh(Linear([q | fc7])) replaces q in the memory attention
+  bool embdrop = false;     // Dropout(0.5) on the word embeddings (mn-*, lf-att-*)
+  bool rnn_layers = false;  // exposes .rnnLayers to the gen decoder's forwardConnect (lf-*, hre*)
 };
 Cfg parse_cfg(const vd_params* p);
 
@@ -208,6 +218,13 @@ struct Engine {
 
   void encoder_forward(const vd_batch* b);
   void encoder_backward(const float* dEnc);
+  // blocks shared by several encoder graphs
+  float *qi_join = nullptr, *qi_proj = nullptr;                 // mn-ques-im-hist: [q | fc7] and tanh(Linear(.))
+  const float* mn_query_in = nullptr;                           // what enters the memory attention as the query (q3 or qi_proj)
+  void mn_block_fwd(const float* qin, const float* h3, float* out);      // MM -> MaskSoftMax -> MM -> fact -> (+q) -> query
+  void mn_block_bwd(const float* dout, const float* out, float* dqin, float* dh3);   // dqin / dh3 are overwritten
+  void san_block_fwd(const float* u0);                          // SAN hops + out layer -> encOut
+  void san_block_bwd(const float* dEnc, float* du0);            // du0 (overwritten) = gradient wrt u0
   void forward_connect();
   void decoder_forward();
   float criterion_forward();
