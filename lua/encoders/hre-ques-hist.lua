@@ -1,14 +1,2 @@
--- Drop-in for /root/reference/encoders/hre-ques-hist.lua: same table shape ({model = ...}), same file name, loaded by
--- model.lua:19-20 with dofile().  The graph itself runs in libvisdial_b200.so (csrc/engine.cu).
-local mod = require 'module_b200'
-local encoderNet = {}
-
-function encoderNet.model(params)
-  assert(params.encoder == 'hre-ques-hist')
-  local enc = mod.newHalf('enc', params, 'hre-ques-hist')
-  enc.wordEmbed = 'wordEmbed.weight'            -- shared table lives in the engine (disc.lua:12, gen.lua:10)
-  enc.rnnLayers = {'ques.lstm1', 'ques.lstm2'}   -- gen.lua:30-42 reads this
-  return enc
-end
-
-return encoderNet
+-- Drop-in for encoders/hre-ques-hist.lua (same file name and table shape; model.lua:19-20 loads it with dofile()).
+return require('module_b200').encoder('hre-ques-hist')

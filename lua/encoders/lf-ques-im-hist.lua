@@ -1,14 +1,2 @@
--- Drop-in for /root/reference/encoders/lf-ques-im-hist.lua: same table shape ({model = ...}), same file name, loaded by
--- model.lua:19-20 with dofile().  The graph itself runs in libvisdial_b200.so (csrc/engine.cu).
-local mod = require 'module_b200'
-local encoderNet = {}
-
-function encoderNet.model(params)
-  assert(params.encoder == 'lf-ques-im-hist')
-  local enc = mod.newHalf('enc', params, 'lf-ques-im-hist')
-  enc.wordEmbed = 'wordEmbed.weight'            -- shared table lives in the engine (disc.lua:12, gen.lua:10)
-  enc.rnnLayers = true and {'ques.lstm1', 'ques.lstm2'} or nil   -- gen.lua:30-42 reads this
-  return enc
-end
-
-return encoderNet
+-- Drop-in for encoders/lf-ques-im-hist.lua (same file name and table shape; model.lua:19-20 loads it with dofile()).
+return require('module_b200').encoder('lf-ques-im-hist')

@@ -53,4 +53,24 @@ function Wrapper:training() vd.check(vd.C.vd_set_training(self.engine, 1)) end
 function Wrapper:evaluate() vd.check(vd.C.vd_set_training(self.engine, 0)) end
 function Wrapper:zeroGradParameters() vd.check(vd.C.vd_zero_grad(self.engine)) end
 
-return {newHalf = newHalf, Wrapper = Wrapper}
+-- What `dofile('encoders/<name>.lua')` returns (model.lua:19-20): {model = function(params) ... end}.  The graph runs in the engine;
+-- the only per-encoder fact left on this side is whether upstream exports enc.rnnLayers (Sequential encoders do, the nngraph
+-- gModule ones — mn-*, lf-att-* — do not), which decoders/gen.lua:30-42 reads to decide on the state copy.
+local exportsRnnLayers = {
+  ['lf-ques'] = true, ['lf-ques-im'] = true, ['lf-ques-hist'] = true, ['lf-ques-im-hist'] = true, ['lf-att-ques-im-hist'] = false,
+  ['hre-ques-hist'] = true, ['hre-ques-im-hist'] = true, ['hrea-ques-im-hist'] = true,
+  ['mn-ques-hist'] = false, ['mn-ques-im-hist'] = false, ['mn-att-ques-im-hist'] = false,
+}
+
+local function encoder(name)
+  assert(exportsRnnLayers[name] ~= nil, 'unknown encoder ' .. name)
+  return {model = function(params)
+    assert(params.encoder == name)
+    local enc = newHalf('enc', params, name)
+    enc.wordEmbed = 'wordEmbed.weight'            -- the shared table lives in the engine (disc.lua:12, gen.lua:10)
+    enc.rnnLayers = exportsRnnLayers[name] and {'ques.lstm1', 'ques.lstm2'} or nil
+    return enc
+  end}
+end
+
+return {newHalf = newHalf, Wrapper = Wrapper, encoder = encoder}
