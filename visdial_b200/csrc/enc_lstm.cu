@@ -4,19 +4,29 @@
 //
 // Why (profiles/r01_ncu_full_encoder_small_steps.md, r02_launches_f16_v1.md): the per-step kernels are latency-bound — 360
 // launches, 8.3 ms of serialised device time per training step for < 1 % of the FLOPs, each launch re-streaming the 4 MB
-// recurrent weight through L2.  Here the weight is STATIONARY: every CTA keeps a 128 KB fp16 slice of it in shared memory
-// for the whole sequence, and per step only the (128-row x K) fp16 state panel moves (TMA, 4-stage ring):
+// recurrent weight through L2.  Here the weight is STATIONARY: every CTA keeps a 128 KB fp16 slice of it (32 hidden units)
+// in shared memory for the whole sequence, and per step only a (128-row x K) fp16 panel moves (TMA, 6-stage ring).  Three
+// CTA roles per 128-row block, H/32 CTAs each, so that NO role contracts more than one panel per step:
 //
-//   layer-1 CTA (slice of 32 hidden units): gates = xproj1[t] (batched GEMM, up front) + h1_{t-1} Wh1^T        K = H
-//   layer-2 CTA (slice of 16 hidden units): gates = [h1_t | h2_{t-1}] [Wx2 | Wh2]^T + b2                       K = 2H
+//   forward   L1  cell of layer 1:   gates = xproj1[t] (batched GEMM, up front) + h1_{t-1} Wh1^T      -> h1_t      K = H
+//             X2  input half of 2:   gates2[t] <- h1_t Wx2^T + b2   (off the recurrent critical path)              K = H
+//             L2  cell of layer 2:   gates = gates2[t] (from X2)    + h2_{t-1} Wh2^T                  -> h2_t      K = H
+//   BPTT      T   cell of layer 2:   dh2_t = da2_{t+1} Wh2 [+ dL/dh2 at the last step]                -> da2_t     K = 4H
+//             X   input half:        da1[t][:, 0:H] <- da2_t Wx2    (partial of dh1_t, parked in the output rows)  K = 4H
+//             B   cell of layer 1:   dh1_t = partial + da1_{t+1} Wh1 [+ dL/dh1 at the last step]      -> da1_t     K = 4H
 //
-// tcgen05 kind::f16, M = 128 rows, N = 4 gates x slice, fp32 accumulators in TMEM; the pointwise half runs in the epilogue
-// warps (thread = row) with the cell state held in REGISTERS across the sequence.  A group of (H/32 + H/16) CTAs owns one
-// 128-row block; groups loop over row blocks.  Time steps are chained through global-memory flags: a CTA publishes
-// "step t of my slice is stored" (fence + atomicAdd), the TMA producer of a consumer CTA spins on the count of the row
-// block (ld.acquire), so layer 2 trails layer 1 by one step (wavefront) with no cluster / grid barrier.  A stuck wait traps.
+// (Measured with the phase trace below, round 2: with the layer-2 cell contracting [h1_t | h2_{t-1}] itself, and the layer-1
+// BPTT cell [da2_t | da1_{t+1}], the two-panel role set the step time: 21.9k clk forward, 45.6k clk BPTT, of which the
+// operand stream — 64 KB in flight per SM against ~2.5k clk of L2 latency — was 12k / 37k.)
 //
-// Numerics: fp16 operands (h, weights) with fp32 accumulation = the VD_MATH_F16 class (10-bit mantissa like TF32); cell
+// tcgen05 kind::f16, M = 128 rows, N = 4 gates x 32 (forward) / 32 (BPTT), fp32 accumulators in TMEM; the pointwise half
+// runs in the epilogue warps (thread = row, 256-bit global accesses) with the cell state / its gradient held in REGISTERS
+// across the sequence.  Time steps are chained through global-memory flags: a CTA publishes "step t of my slice is stored"
+// (fence + atomicAdd), the TMA producer (and, for the parked partials, the epilogue threads) of a consumer CTA spin on the
+// count of the row block (ld.acquire) — no cluster / grid barrier.  A stuck wait traps.  All CTAs must be co-resident
+// (3 H/32 x row-block groups <= SM count, one CTA per SM): enc_pair_shape_ok.
+//
+// Numerics: fp16 operands (h, da, weights) with fp32 accumulation = the VD_MATH_F16 class (10-bit mantissa like TF32); cell
 // state, gate pre-activations, saved activations and all gradients fp32.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -28,10 +38,12 @@ namespace vd {
 namespace tc {
 
 constexpr int EP_THREADS = 192;          // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (thread = row)
-constexpr int EP_STAGES = 4;
+constexpr int EP_STAGES = 6;
 constexpr int EP_STAGE_BYTES = 128 * 64 * 2;      // 128 rows x 64 halves
-constexpr int EP_W_BYTES_MAX = 131072;            // weight slice: N x K x 2 B = 256*H bytes (H <= 512)
+constexpr int EP_W_BYTES_MAX = 131072;            // weight slice: fwd 128 x H, BPTT 32 x 4H halves = 256*H bytes (H <= 512)
 constexpr int EP_SMEM = EP_W_BYTES_MAX + EP_STAGES * EP_STAGE_BYTES + 1024 + 256;
+constexpr int EP_HS = 32;                         // hidden units per CTA slice
+static_assert(EP_SMEM <= 227 * 1024, "persistent encoder LSTM: shared memory budget");
 
 __host__ __device__ constexpr uint32_t ep_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -51,7 +63,7 @@ __device__ __forceinline__ uint4 ep_pack8(const float* v) {
   return make_uint4(ep_pack2(v[0], v[1]), ep_pack2(v[2], v[3]), ep_pack2(v[4], v[5]), ep_pack2(v[6], v[7]));
 }
 // spin until *flag >= want (published with fence + atomicAdd by the producers of that step); traps instead of hanging
-__device__ __forceinline__ void wait_flag(const int* flag, int want) {
+__device__ __forceinline__ void wait_flag_generic(const int* flag, int want) {
   uint32_t spins = 0;
   for (;;) {
     int v;
@@ -60,448 +72,550 @@ __device__ __forceinline__ void wait_flag(const int* flag, int want) {
     if (++spins > 64) __nanosleep(40);
     if (spins > (1u << 27)) __trap();
   }
+}
+__device__ __forceinline__ void wait_flag(const int* flag, int want) {
+  wait_flag_generic(flag, want);
   asm volatile("fence.proxy.async;" ::: "memory");       // the TMA (async proxy) reads what generic-proxy stores published
 }
+// thread = row: each thread touches its own 32-byte piece of a row.  One 256-bit access per piece (sm_100: LDG/STG.256) — the
+// epilogues are bound by LSU wavefronts (one per distinct line per instruction), not by bytes
 __device__ __forceinline__ void ld8g(const float* p, float* d) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
-  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st8g(float* p, const float* v) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
+
+// one 128-byte line of a row per call (4 consecutive 256-bit accesses of the same thread: the LSU merges them far better than the same
+// bytes issued as 32-byte pieces of four different lines — measured: 140 vs 370 clk per store instruction and warp)
+__device__ __forceinline__ void ld32g(const float* p, float* d) { ld8g(p, d); ld8g(p + 8, d + 8); ld8g(p + 16, d + 16); ld8g(p + 24, d + 24); }
+__device__ __forceinline__ void st32g(float* p, const float* v) { st8g(p, v); st8g(p + 8, v + 8); st8g(p + 16, v + 16); st8g(p + 24, v + 24); }
+__device__ __forceinline__ void st32h(__half* p, const float* v) {            // 32 halves = 64 bytes
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(ep_pack2(v[0], v[1])), "r"(ep_pack2(v[2], v[3])), "r"(ep_pack2(v[4], v[5])), "r"(ep_pack2(v[6], v[7])),
+                 "r"(ep_pack2(v[8], v[9])), "r"(ep_pack2(v[10], v[11])), "r"(ep_pack2(v[12], v[13])), "r"(ep_pack2(v[14], v[15])) : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p + 16), "r"(ep_pack2(v[16], v[17])), "r"(ep_pack2(v[18], v[19])), "r"(ep_pack2(v[20], v[21])), "r"(ep_pack2(v[22], v[23])),
+                 "r"(ep_pack2(v[24], v[25])), "r"(ep_pack2(v[26], v[27])), "r"(ep_pack2(v[28], v[29])), "r"(ep_pack2(v[30], v[31])) : "memory");
+}
+__device__ __forceinline__ void zero32(float* d) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) d[e] = 0.f;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  tmem_ld8(taddr, v); tmem_ld8(taddr + 8, v + 8); tmem_ld8(taddr + 16, v + 16); tmem_ld8(taddr + 24, v + 24);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  tmem_st8(taddr, v); tmem_st8(taddr + 8, v + 8); tmem_st8(taddr + 16, v + 16); tmem_st8(taddr + 24, v + 24);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Optional phase trace (VD_ENC_TRACE=1, debugging only): per (CTA, step) stamps — clock64 at {0: flag seen, 1: panel issued, 2: accumulator
+// free, 3: last operand chunk landed + MMAs issued, 4: accumulator ready, 5: epilogue math + stores issued, 6: published} and globaltimer at
+// {7: published, 8: flag seen}.  A null pointer (the normal case) costs one predicated branch per stamp.
+constexpr int EP_TRACE_SLOTS = 10;
+__device__ __forceinline__ void ep_stamp(unsigned long long* trace, int T, int t, int slot, bool wall = false) {
+  if (trace) {
+    unsigned long long v;
+    if (wall) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    else v = (unsigned long long)clock64();
+    trace[((size_t)blockIdx.x * T + t) * EP_TRACE_SLOTS + slot] = v;
+  }
+}
+
+enum { EP_CELL1 = 0, EP_PROJ = 1, EP_CELL2 = 2 };      // forward: L1, X2, L2;  BPTT: T (layer 2), X, B (layer 1) — see the header
 
 struct EncFwdParams {
   int T, R, H, RB;                 // RB = number of 128-row blocks
-  int nS1, nS2, groups;            // slices of layer 1 (H/32), layer 2 (H/16); CTA groups (each owns row blocks g, g+groups, ...)
+  int nS, groups;                  // slices per role (H/32); CTA groups of 3 nS (each owns row blocks g, g+groups, ...)
   float* gates1; float* c1; float* h1; __half* h1_16;      // gates1: in = x-projection (+bias), out = activated gates
-  float* gates2; float* c2; float* h2; __half* h2_16;
+  float* gates2; float* c2; float* h2; __half* h2_16;      // gates2: parked x-half (+bias) per step, then activated gates
   const float* bias2;
   const int32_t* mask;             // (T,R) token ids for maskzero, or null
-  int* flags;                      // [2][RB][T]: completed slices of (layer, row block, step)
+  int* flags;                      // [3][RB][T]: completed slices of (role, row block, step)
+  unsigned long long* trace;       // null, or [grid][T][EP_TRACE_SLOTS]
 };
+
+// carve-up shared by both kernels
+struct EpSmem {
+  uint8_t* wsm; uint8_t* stages; uint64_t* full; uint64_t* empty; uint64_t* tfull; uint64_t* tempty; uint64_t* wbar; uint64_t* seen; uint32_t* tmem_slot;
+  __device__ explicit EpSmem(uint8_t* raw) {
+    uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    wsm = smem;                                               // resident weight slice: k-block tiles of [N rows][128 B]
+    stages = smem + EP_W_BYTES_MAX;
+    full = (uint64_t*)(stages + EP_STAGES * EP_STAGE_BYTES);
+    empty = full + EP_STAGES;
+    tfull = empty + EP_STAGES;
+    tempty = tfull + 1;
+    wbar = tempty + 1;
+    seen = wbar + 1;                                          // producer -> epilogue: "the flag of the next step has been seen"
+    tmem_slot = (uint32_t*)(seen + 1);
+  }
+  __device__ void init_barriers() {
+    for (int s = 0; s < EP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 4); mbar_init(wbar, 1); mbar_init(seen, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+};
+
+// MMA issuer of one step: KB k-blocks of the streamed panel against the resident slice, accumulator <- (not accumulate) on the first
+// k-block order of a CTA: rotated by `koff`, so that the CTAs streaming the same panel at the same moment (the H/32 slices of a role, and the
+// projection role beside the cell that shares its panel) ask L2 for different lines instead of queueing on the same ones
+__device__ __forceinline__ int ep_koff(int role, int slice, int nS, int KB) {
+  const int stride = KB >= 2 * nS ? KB / (2 * nS) : 1;
+  return ((2 * slice + (role == EP_PROJ ? 1 : 0)) * stride) % KB;
+}
+__device__ __forceinline__ void ep_mma_step(const EpSmem& sm, uint32_t tmem_base, uint32_t idesc, int KB, int koff, int n_rows, int lane, int& s,
+                                            uint32_t& ph, unsigned long long* trace, int T, int t) {
+  uint32_t first = 1;
+  for (int kb = 0; kb < KB; ++kb) {
+    mbar_wait(&sm.full[s], ph);
+    tc_fence_after();
+    if (lane == 0) {
+      int kr = kb + koff; if (kr >= KB) kr -= KB;
+      const uint32_t sa = smem_u32(sm.stages + s * EP_STAGE_BYTES);
+      const uint32_t sb = smem_u32(sm.wsm + kr * n_rows * 128);
+      const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ep_umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+        first = 0;
+      }
+      umma_commit(&sm.empty[s]);
+      if (kb == KB - 1) { umma_commit(sm.tfull); ep_stamp(trace, T, t, 3); }
+    }
+    __syncwarp();
+    first = 0;
+    if (++s == EP_STAGES) { s = 0; ph ^= 1; }
+  }
+}
+
+// publish step t of this slice: barrier of the epilogue warps, then ONE gpu-scope release (cumulative over what the barrier made
+// visible to the signalling thread) that counts the slice in — the grid-sync idiom of cooperative groups
+__device__ __forceinline__ void ep_publish(int* flag, unsigned long long* trace, int T, int t) {
+  if (threadIdx.x == 64) ep_stamp(trace, T, t, 5);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x == 64) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
+    ep_stamp(trace, T, t, 6); ep_stamp(trace, T, t, 7, true);
+  }
+}
 
 __global__ void __launch_bounds__(EP_THREADS, 1)
 k_enc_pair_fwd(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const EncFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem;                                        // resident weight slice: KBW tiles of [N rows][128 B]
-  uint8_t* stages = smem + EP_W_BYTES_MAX;
-  uint64_t* full = (uint64_t*)(stages + EP_STAGES * EP_STAGE_BYTES);
-  uint64_t* empty = full + EP_STAGES;
-  uint64_t* tfull = empty + EP_STAGES;
-  uint64_t* tempty = tfull + 1;
-  uint64_t* wbar = tempty + 1;
-  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
-
+  EpSmem sm(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, T = p.T;
-  const int per_group = p.nS1 + p.nS2;
+  const int per_group = 3 * p.nS;
   const int group = blockIdx.x / per_group, idx = blockIdx.x % per_group;
-  const int layer = idx < p.nS1 ? 0 : 1;
-  const int slice = layer == 0 ? idx : idx - p.nS1;
-  const int HS = layer == 0 ? 32 : 16;             // hidden units of this slice
-  const int N = 4 * HS;                            // accumulator columns [i | f | o | g]
-  const int KB1 = H / 64;                          // k-blocks of one H-wide operand
-  const int KBW = layer == 0 ? KB1 : 2 * KB1;      // k-blocks of the resident weight slice
-  int* flag1 = p.flags;
-  int* flag2 = p.flags + (size_t)p.RB * T;
+  const int role = idx / p.nS, slice = idx % p.nS;
+  constexpr int HS = EP_HS, N = 4 * EP_HS;          // accumulator columns [i | f | o | g]
+  const int KB = H / 64;                           // k-blocks of the streamed panel = of the resident slice
+  const int koff = ep_koff(role, slice, p.nS, KB);
+  int* flagL1 = p.flags;
+  int* flagX = p.flags + (size_t)p.RB * T;
+  int* flagL2 = p.flags + 2 * (size_t)p.RB * T;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < EP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tfull, 1); mbar_init(tempty, 4); mbar_init(wbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  if (threadIdx.x == 0) sm.init_barriers();
+  if (warp == 1) tmem_alloc(sm.tmem_slot, 256);        // [0,128) accumulator, [128,256) staging of the activated gates (cell roles)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- weights, once: tile kb = 4 gate boxes of HS rows x 64 halves
-      mbar_expect_tx(wbar, (uint32_t)(KBW * N * 128));
-      for (int kb = 0; kb < KBW; ++kb)
-        for (int g = 0; g < 4; ++g)
-          tma_load_2d(wsm + kb * N * 128 + g * HS * 128, layer == 0 ? &tmW1 : &tmW2, wbar, kb * 64, g * H + slice * HS);
-      // ---- per step: the state panel(s) of this row block
+      // ---- weights, once: tile kb = 4 gate boxes of HS rows x 64 halves.  W1 = Wh1 [4H, H]; W2 = [Wx2 | Wh2] [4H, 2H]
+      const CUtensorMap* tw = role == EP_CELL1 ? &tmW1 : &tmW2;
+      const int kofs = role == EP_CELL2 ? H : 0;
+      mbar_expect_tx(sm.wbar, (uint32_t)(KB * N * 128));
+      for (int kb = 0; kb < KB; ++kb)
+        for (int g = 0; g < 4; ++g) tma_load_2d(sm.wsm + kb * N * 128 + g * HS * 128, tw, sm.wbar, kofs + kb * 64, g * H + slice * HS);
+      // ---- per step: the state panel of this row block
       int s = 0; uint32_t ph = 0;
-      auto load_panel = [&](const CUtensorMap* tm, int row0) {
-        for (int kb = 0; kb < KB1; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], EP_STAGE_BYTES);
-          tma_load_2d(stages + s * EP_STAGE_BYTES, tm, &full[s], kb * 64, row0);
-          if (++s == EP_STAGES) { s = 0; ph ^= 1; }
-        }
-      };
       for (int rb = group; rb < p.RB; rb += p.groups) {
         for (int t = 0; t < T; ++t) {
-          if (layer == 0) {
+          const CUtensorMap* tm; int ts;
+          if (role == EP_PROJ) { wait_flag(flagL1 + (size_t)rb * T + t, p.nS); tm = &tmH1; ts = t; }
+          else {
             if (t == 0) continue;
-            wait_flag(flag1 + (size_t)rb * T + (t - 1), p.nS1);
-            load_panel(&tmH1, (t - 1) * p.R + rb * 128);
-          } else {
-            if (t > 0) {                                    // recurrent half first: it is ready one step earlier
-              wait_flag(flag2 + (size_t)rb * T + (t - 1), p.nS2);
-              load_panel(&tmH2, (t - 1) * p.R + rb * 128);
-            }
-            wait_flag(flag1 + (size_t)rb * T + t, p.nS1);
-            load_panel(&tmH1, t * p.R + rb * 128);
+            wait_flag((role == EP_CELL1 ? flagL1 : flagL2) + (size_t)rb * T + (t - 1), p.nS);
+            tm = role == EP_CELL1 ? &tmH1 : &tmH2; ts = t - 1;
           }
+          ep_stamp(p.trace, T, t, 8, true); ep_stamp(p.trace, T, t, 0);
+          if (role != EP_PROJ) mbar_arrive(sm.seen);
+          for (int kb = 0; kb < KB; ++kb) {
+            int kr = kb + koff; if (kr >= KB) kr -= KB;
+            mbar_wait(&sm.empty[s], ph ^ 1);
+            mbar_expect_tx(&sm.full[s], EP_STAGE_BYTES);
+            tma_load_2d(sm.stages + s * EP_STAGE_BYTES, tm, &sm.full[s], kr * 64, ts * p.R + rb * 128);
+            if (++s == EP_STAGES) { s = 0; ph ^= 1; }
+          }
+          ep_stamp(p.trace, T, t, 1);
         }
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: same (row block, step, panel, k-block) order as the producer
+    // ---- MMA issuer: same (row block, step, k-block) order as the producer
     const uint32_t idesc = ep_idesc_f16(128, N);
-    mbar_wait(wbar, 0);
+    mbar_wait(sm.wbar, 0);
     tc_fence_after();
     int s = 0; uint32_t ph = 0; uint32_t nuse = 0;
     for (int rb = group; rb < p.RB; rb += p.groups) {
       for (int t = 0; t < T; ++t) {
-        const int npan = layer == 0 ? (t > 0 ? 1 : 0) : (t > 0 ? 2 : 1);
-        if (npan == 0) continue;
-        mbar_wait(tempty, (nuse & 1) ^ 1);                   // the epilogue has drained the accumulator of the previous step
+        if (role != EP_PROJ && t == 0) continue;
+        mbar_wait(sm.tempty, (nuse & 1) ^ 1);                // the epilogue has drained the accumulator of the previous step
         tc_fence_after();
         ++nuse;
-        uint32_t first = 1;
-        for (int pan = 0; pan < npan; ++pan) {
-          // weight k-blocks: layer 1 -> 0..KB1-1; layer 2 -> recurrent half KB1..2KB1-1 first (when present), then the x half
-          const int kb0 = layer == 0 ? 0 : ((npan == 2 && pan == 0) ? KB1 : 0);
-          for (int kb = 0; kb < KB1; ++kb) {
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t sa = smem_u32(stages + s * EP_STAGE_BYTES);
-              const uint32_t sb = smem_u32(wsm + (kb0 + kb) * N * 128);
-              const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                ep_umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-                first = 0;
-              }
-              umma_commit(&empty[s]);
-              if (pan == npan - 1 && kb == KB1 - 1) umma_commit(tfull);
-            }
-            __syncwarp();
-            first = 0;
-            if (++s == EP_STAGES) { s = 0; ph ^= 1; }
-          }
-        }
+        if (lane == 0) ep_stamp(p.trace, T, t, 2);
+        ep_mma_step(sm, tmem_base, idesc, KB, koff, N, lane, s, ph, p.trace, T, t);
       }
     }
   } else {
-    // ---- epilogue: thread = row of the 128-row block; cell state in registers across the sequence
+    // ---- epilogue: thread = row of the 128-row block
     const int q = warp & 3;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int j0 = slice * HS;
-    float* gates = layer == 0 ? p.gates1 : p.gates2;
-    float* cst = layer == 0 ? p.c1 : p.c2;
-    float* hst = layer == 0 ? p.h1 : p.h2;
-    __half* h16 = layer == 0 ? p.h1_16 : p.h2_16;
-    int* flag = layer == 0 ? flag1 : flag2;
-    uint32_t nuse = 0;
-    for (int rb = group; rb < p.RB; rb += p.groups) {
-      const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
-      const bool row_ok = row < p.R;
-      float c[32];
+    uint32_t nuse = 0, nseen = 0;
+    if (role == EP_PROJ) {
+      // gates2[t] <- h1_t Wx2^T + b2 for the 4 x 32 gate columns of this slice (the layer-2 cell of the same slice adds its recurrent half)
+      for (int rb = group; rb < p.RB; rb += p.groups) {
+        const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
+        const bool row_ok = row < p.R;
+        for (int t = 0; t < T; ++t) {
+          const int64_t tr = (int64_t)t * p.R + row;
+          mbar_wait(sm.tfull, nuse & 1); tc_fence_after(); ++nuse;
+          if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 4);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) c[e] = 0.f;
-      for (int t = 0; t < T; ++t) {
-        const bool has_acc = layer == 1 || t > 0;
-        const int64_t tr = (int64_t)t * p.R + row;
-        const float keep = (row_ok && p.mask && p.mask[tr] == 0) ? 0.f : 1.f;
-        const int nsub = HS / 8;
-        // additive term of the pre-activation: layer 1 = this step's x-projection (+ bias) rows, layer 2 = the bias.  The
-        // loads of sub-tile s+1 are issued before the math of sub-tile s, those of sub-tile 0 before the accumulator is awaited.
-        float xn[4][8];
-        auto load_x = [&](int sub) {
-          const int j = j0 + sub * 8;
+          for (int g = 0; g < 4; ++g) {                        // one gate = one 128-byte line of the row per pass
+            float a[HS], bb[HS];
+            tmem_ld32(taddr + g * HS, a);
+            ld32g(p.bias2 + g * H + j0, bb);
+            tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (!row_ok) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) xn[g][e] = 0.f;
-            } else if (layer == 0) ld8g(gates + tr * 4 * H + g * H + j, xn[g]);
-            else ld8g(p.bias2 + g * H + j, xn[g]);
+            for (int e = 0; e < HS; ++e) a[e] += bb[e];
+            if (row_ok) st32g(p.gates2 + tr * 4 * H + g * H + j0, a);
           }
-        };
-        load_x(0);
-        if (layer == 0 && row_ok && t + 1 < T) {             // next step's x-projection rows: pull them into L2 now
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gates + (tr + p.R) * 4 * H + g * H + j0) : "memory");
-        }
-        if (has_acc) { mbar_wait(tfull, nuse & 1); tc_fence_after(); ++nuse; }
-#pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-          if (sub < nsub) {
-            float a[4][8], hn[8];
-            if (has_acc) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * HS + sub * 8, a[g]);
-              tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[g][e] = 0.f;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[g][e] += xn[g][e];
-            if (sub + 1 < nsub) load_x(sub + 1);
-            const int j = j0 + sub * 8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float gi = fsigmoid(a[0][e]), gf = fsigmoid(a[1][e]), go = fsigmoid(a[2][e]), gg = ftanh(a[3][e]);
-              const float c_ = (gf * c[sub * 8 + e] + gi * gg) * keep;       // maskzero: state reset on an all-zero input row
-              a[0][e] = gi * keep; a[1][e] = gf * keep; a[2][e] = go * keep; a[3][e] = gg * keep;
-              c[sub * 8 + e] = c_;
-              hn[e] = go * ftanh(c_) * keep;
-            }
-            if (row_ok) {
-              *reinterpret_cast<uint4*>(h16 + tr * H + j) = ep_pack8(hn);   // what the next step's TMA reads goes out first
-#pragma unroll
-              for (int g = 0; g < 4; ++g) st8g(gates + tr * 4 * H + g * H + j, a[g]);
-              st8g(cst + tr * H + j, &c[sub * 8]);
-              st8g(hst + tr * H + j, hn);
-            }
-          }
-        }
-        if (has_acc) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
+          if (lane == 0) mbar_arrive(sm.tempty);
+          ep_publish(flagX + (size_t)rb * T + t, p.trace, T, t);
         }
-        // publish step t of this slice: CTA barrier, then ONE gpu-scope fence (cumulative over what the barrier made
-        // visible to the signalling thread) and the count-in — the grid-sync idiom of cooperative groups
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          __threadfence();
-          atomicAdd(flag + (size_t)rb * T + t, 1);
+      }
+    } else {
+      // LSTM cell, state c in registers across the sequence.  One gate at a time over all 32 units of the slice (order i, g, f, o), so
+      // that every global access of a thread is a whole 128-byte line; the activated gates wait in TMEM (staging columns) until h_t is
+      // out and published — only the 64 bytes of h16 per row are stored ahead of the flag, the 768 bytes of saved state after it,
+      // while the consumers are already streaming the panel
+      const bool l1 = role == EP_CELL1;
+      float* gates = l1 ? p.gates1 : p.gates2;
+      float* cst = l1 ? p.c1 : p.c2;
+      float* hst = l1 ? p.h1 : p.h2;
+      __half* h16 = l1 ? p.h1_16 : p.h2_16;
+      int* flag = l1 ? flagL1 : flagL2;
+      const uint32_t tstage = taddr + 128;
+      for (int rb = group; rb < p.RB; rb += p.groups) {
+        const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
+        const bool row_ok = row < p.R;
+        float c[HS];
+        zero32(c);
+        for (int t = 0; t < T; ++t) {
+          const bool has_acc = t > 0;
+          const int64_t tr = (int64_t)t * p.R + row;
+          const float keep = (row_ok && p.mask && p.mask[tr] == 0) ? 0.f : 1.f;
+          // additive term of the pre-activation: the x-half (+ bias) rows — layer 1: batched GEMM before the kernel; layer 2: parked in
+          // gates2[t] by the projection CTAs of this step (acquire their count first).  Gate i's line is requested before the accumulator
+          // is awaited, every other gate's line one pass ahead of its use.
+          if (!l1) wait_flag_generic(flagX + (size_t)rb * T + t, p.nS);
+          float* xrow = gates + tr * 4 * H + j0;
+          float x[HS], a[HS], ig[HS];
+          // the four x lines go to the TMEM staging columns while the contraction of this step is still running: the passes below then
+          // read both summands from TMEM (~100 clk) instead of stalling on L2 (~1.5k clk) once per gate
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (row_ok) ld32g(xrow + g * H, x); else zero32(x);
+            tmem_st32(tstage + g * HS, x);
+          }
+          tmem_st_wait();
+          if (l1 && row_ok && t + 1 < T) {                     // next step's x-projection rows: pull them into L2 now
+#pragma unroll
+            for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + (int64_t)p.R * 4 * H + g * H) : "memory");
+          }
+          if (has_acc) { mbar_wait(sm.tfull, nuse & 1); tc_fence_after(); ++nuse; }
+          if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 4);
+          // ---- i
+          if (has_acc) tmem_ld32(taddr + 0 * HS, a); else zero32(a);
+          tmem_ld32(tstage + 0 * HS, x); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HS; ++e) { a[e] = fsigmoid(a[e] + x[e]) * keep; ig[e] = a[e]; }
+          tmem_st32(tstage + 0 * HS, a);
+          // ---- g
+          if (has_acc) tmem_ld32(taddr + 3 * HS, a); else zero32(a);
+          tmem_ld32(tstage + 3 * HS, x); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HS; ++e) { a[e] = ftanh(a[e] + x[e]) * keep; ig[e] *= a[e]; }
+          tmem_st32(tstage + 3 * HS, a);
+          // ---- f  (maskzero: keep = 0 resets the state of an all-zero input row)
+          if (has_acc) tmem_ld32(taddr + 1 * HS, a); else zero32(a);
+          tmem_ld32(tstage + 1 * HS, x); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HS; ++e) { a[e] = fsigmoid(a[e] + x[e]) * keep; c[e] = (a[e] * c[e] + ig[e]) * keep; }
+          tmem_st32(tstage + 1 * HS, a);
+          // ---- o, h
+          if (has_acc) tmem_ld32(taddr + 2 * HS, a); else zero32(a);
+          tmem_ld32(tstage + 2 * HS, x); tmem_ld_wait();
+          if (has_acc) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sm.tempty);             // the accumulator is drained: the next step's MMAs may start
+          }
+#pragma unroll
+          for (int e = 0; e < HS; ++e) { a[e] = fsigmoid(a[e] + x[e]) * keep; ig[e] = a[e] * ftanh(c[e]) * keep; }     // ig <- h_t
+          tmem_st32(tstage + 2 * HS, a);
+          if (row_ok) st32h(h16 + tr * H + j0, ig);             // what the next step's TMA reads: the only store ahead of the flag
+          ep_publish(flag + (size_t)rb * T + t, p.trace, T, t);
+          // ---- after the flag: saved state for the backward pass (activated gates from the staging columns, c_t, h_t) — held back until
+          // this CTA's producer has seen the next step's flag, so that its polling loads do not queue behind these 768 bytes per row
+          if (t + 1 < T) { mbar_wait(sm.seen, nseen & 1); ++nseen; }
+          tmem_st_wait();
+          if (row_ok) { st32g(cst + tr * H + j0, c); st32g(hst + tr * H + j0, ig); }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            tmem_ld32(tstage + g * HS, a); tmem_ld_wait();
+            if (row_ok) st32g(xrow + g * H, a);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 
 // ------------------------------------------------------------------------------------------------
-// BPTT of the pair, same structure mirrored in time and in roles:
-//   layer-2 CTA (slice of 32 hidden units): dh2_t = da2_{t+1} Wh2            (K = 4H)  [+ dL/dh2 at the last step]
-//   layer-1 CTA (slice of 16 hidden units): dh1_t = da2_t Wx2 + da1_{t+1} Wh1 (K = 8H)  [+ dL/dh1 at the last step]
-// then the SeqLSTM backward pointwise (saved gates, c_{t-1}, c_t; dc carried in registers) -> da_t as fp32 (what the weight /
-// input gradients after the kernel read) and fp16 (the A operand of the steps that follow).  Layer 2 runs ahead of layer 1;
-// layer 1's producer streams the da2_t half first (ready early) and the da1_{t+1} half when its own previous step is published.
+// BPTT of the pair, same structure mirrored in time (roles T / X / B of the header).  The SeqLSTM backward pointwise reads the saved
+// gates, c_{t-1}, c_t, carries dc in registers and writes da_t as fp32 (what the weight / input gradients after the kernel read) and
+// fp16 (the A operand of the steps that follow).  Layer 2 runs ahead; the X CTAs turn each da2_t into the layer-1 partial right behind it.
 struct EncBwdParams {
   int T, R, H, RB;
-  int nS1, nS2, groups;            // slices of layer 1 (H/16), layer 2 (H/32)
+  int nS, groups;
   const float* gates1; const float* c1; float* da1; __half* da1_16;
   const float* gates2; const float* c2; float* da2; __half* da2_16;
   const float* dh_last1; const float* dc_last1; const float* dh_last2; const float* dc_last2;   // (R,H) each or null
   const int32_t* mask;
-  int* flags;                      // [2][RB][T]
+  int* flags;                      // [3][RB][T]
+  unsigned long long* trace;       // null, or [grid][T][EP_TRACE_SLOTS]
 };
 
 __global__ void __launch_bounds__(EP_THREADS, 1)
 k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const EncBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem;
-  uint8_t* stages = smem + EP_W_BYTES_MAX;
-  uint64_t* full = (uint64_t*)(stages + EP_STAGES * EP_STAGE_BYTES);
-  uint64_t* empty = full + EP_STAGES;
-  uint64_t* tfull = empty + EP_STAGES;
-  uint64_t* tempty = tfull + 1;
-  uint64_t* wbar = tempty + 1;
-  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
-
+  EpSmem sm(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, T = p.T;
-  const int per_group = p.nS1 + p.nS2;
+  const int per_group = 3 * p.nS;
   const int group = blockIdx.x / per_group, idx = blockIdx.x % per_group;
-  const int layer = idx < p.nS2 ? 1 : 0;                  // 1 = layer 2 (top), 0 = layer 1
-  const int slice = layer == 1 ? idx : idx - p.nS2;
-  const int HS = layer == 1 ? 32 : 16;                    // hidden units (= accumulator columns) of this slice
-  const int KBP = 4 * H / 64;                             // k-blocks of one (rows, 4H) da panel
-  const int KBW = layer == 1 ? KBP : 2 * KBP;             // k-blocks of the resident weight slice
-  int* flag1 = p.flags;
-  int* flag2 = p.flags + (size_t)p.RB * T;
+  const int role = idx / p.nS, slice = idx % p.nS;         // EP_CELL1 = T (layer 2), EP_PROJ = X, EP_CELL2 = B (layer 1)
+  constexpr int HS = EP_HS;                                // hidden units (= accumulator columns) of this slice
+  const int KB = 4 * H / 64;                               // k-blocks of one (rows, 4H) da panel = of the resident slice
+  const int koff = ep_koff(role, slice, p.nS, KB);
+  int* flagT = p.flags;
+  int* flagX = p.flags + (size_t)p.RB * T;
+  int* flagB = p.flags + 2 * (size_t)p.RB * T;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < EP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tfull, 1); mbar_init(tempty, 4); mbar_init(wbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  if (threadIdx.x == 0) sm.init_barriers();
+  if (warp == 1) tmem_alloc(sm.tmem_slot, 256);        // [0,32) accumulator, [32,256) seven staging slots (cell roles)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(wbar, (uint32_t)(KBW * HS * 128));
-      for (int kb = 0; kb < KBW; ++kb)
-        tma_load_2d(wsm + kb * HS * 128, layer == 1 ? &tmW2 : &tmW1, wbar, kb * 64, slice * HS);
+      // W2 = Wh2 as [H, 4H]; W1 = [Wx2 | Wh1] as [H, 8H]
+      const CUtensorMap* tw = role == EP_CELL1 ? &tmW2 : &tmW1;
+      const int kofs = role == EP_CELL2 ? 4 * H : 0;
+      mbar_expect_tx(sm.wbar, (uint32_t)(KB * HS * 128));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sm.wsm + kb * HS * 128, tw, sm.wbar, kofs + kb * 64, slice * HS);
       int s = 0; uint32_t ph = 0;
-      auto load_panel = [&](const CUtensorMap* tm, int row0) {
-        for (int kb = 0; kb < KBP; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], EP_STAGE_BYTES);
-          tma_load_2d(stages + s * EP_STAGE_BYTES, tm, &full[s], kb * 64, row0);
-          if (++s == EP_STAGES) { s = 0; ph ^= 1; }
-        }
-      };
       for (int rb = group; rb < p.RB; rb += p.groups) {
         for (int t = T - 1; t >= 0; --t) {
-          if (layer == 1) {
+          const CUtensorMap* tm; int ts;
+          if (role == EP_PROJ) { wait_flag(flagT + (size_t)rb * T + t, p.nS); tm = &tmA2; ts = t; }
+          else {
             if (t == T - 1) continue;
-            wait_flag(flag2 + (size_t)rb * T + (t + 1), p.nS2);
-            load_panel(&tmA2, (t + 1) * p.R + rb * 128);
-          } else {
-            wait_flag(flag2 + (size_t)rb * T + t, p.nS2);            // da2_t: the layer above is ahead
-            load_panel(&tmA2, t * p.R + rb * 128);
-            if (t < T - 1) {
-              wait_flag(flag1 + (size_t)rb * T + (t + 1), p.nS1);
-              load_panel(&tmA1, (t + 1) * p.R + rb * 128);
-            }
+            wait_flag((role == EP_CELL1 ? flagT : flagB) + (size_t)rb * T + (t + 1), p.nS);
+            tm = role == EP_CELL1 ? &tmA2 : &tmA1; ts = t + 1;
           }
+          ep_stamp(p.trace, T, t, 8, true); ep_stamp(p.trace, T, t, 0);
+          if (role != EP_PROJ) mbar_arrive(sm.seen);
+          for (int kb = 0; kb < KB; ++kb) {
+            int kr = kb + koff; if (kr >= KB) kr -= KB;
+            mbar_wait(&sm.empty[s], ph ^ 1);
+            mbar_expect_tx(&sm.full[s], EP_STAGE_BYTES);
+            tma_load_2d(sm.stages + s * EP_STAGE_BYTES, tm, &sm.full[s], kr * 64, ts * p.R + rb * 128);
+            if (++s == EP_STAGES) { s = 0; ph ^= 1; }
+          }
+          ep_stamp(p.trace, T, t, 1);
         }
       }
     }
   } else if (warp == 1) {
     const uint32_t idesc = ep_idesc_f16(128, HS);
-    mbar_wait(wbar, 0);
+    mbar_wait(sm.wbar, 0);
     tc_fence_after();
     int s = 0; uint32_t ph = 0; uint32_t nuse = 0;
     for (int rb = group; rb < p.RB; rb += p.groups) {
       for (int t = T - 1; t >= 0; --t) {
-        const int npan = layer == 1 ? (t < T - 1 ? 1 : 0) : (t < T - 1 ? 2 : 1);
-        if (npan == 0) continue;
-        mbar_wait(tempty, (nuse & 1) ^ 1);
+        if (role != EP_PROJ && t == T - 1) continue;
+        mbar_wait(sm.tempty, (nuse & 1) ^ 1);
         tc_fence_after();
         ++nuse;
-        uint32_t first = 1;
-        for (int pan = 0; pan < npan; ++pan) {
-          const int kb0 = pan * KBP;                       // layer 1: panel 0 = Wx2 half, panel 1 = Wh1 half; layer 2: Wh2
-          for (int kb = 0; kb < KBP; ++kb) {
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t sa = smem_u32(stages + s * EP_STAGE_BYTES);
-              const uint32_t sb = smem_u32(wsm + (kb0 + kb) * HS * 128);
-              const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                ep_umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-                first = 0;
-              }
-              umma_commit(&empty[s]);
-              if (pan == npan - 1 && kb == KBP - 1) umma_commit(tfull);
-            }
-            __syncwarp();
-            first = 0;
-            if (++s == EP_STAGES) { s = 0; ph ^= 1; }
-          }
-        }
+        if (lane == 0) ep_stamp(p.trace, T, t, 2);
+        ep_mma_step(sm, tmem_base, idesc, KB, koff, HS, lane, s, ph, p.trace, T, t);
       }
     }
   } else {
     const int q = warp & 3;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int j0 = slice * HS;
-    const float* gates = layer == 1 ? p.gates2 : p.gates1;
-    const float* cst = layer == 1 ? p.c2 : p.c1;
-    float* da = layer == 1 ? p.da2 : p.da1;
-    __half* da16 = layer == 1 ? p.da2_16 : p.da1_16;
-    const float* dh_last = layer == 1 ? p.dh_last2 : p.dh_last1;
-    const float* dc_last = layer == 1 ? p.dc_last2 : p.dc_last1;
-    int* flag = layer == 1 ? flag2 : flag1;
-    uint32_t nuse = 0;
-    for (int rb = group; rb < p.RB; rb += p.groups) {
-      const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
-      const bool row_ok = row < p.R;
-      float dc[32];
+    uint32_t nuse = 0, nseen = 0;
+    if (role == EP_PROJ) {
+      // partial of dh1_t = da2_t Wx2, parked in the first H columns of da1[t] (the B cell of the same slice reads it, then overwrites)
+      for (int rb = group; rb < p.RB; rb += p.groups) {
+        const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
+        const bool row_ok = row < p.R;
+        for (int t = T - 1; t >= 0; --t) {
+          const int64_t tr = (int64_t)t * p.R + row;
+          mbar_wait(sm.tfull, nuse & 1); tc_fence_after(); ++nuse;
+          if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 4);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) dc[e] = 0.f;
-      for (int t = T - 1; t >= 0; --t) {
-        const bool has_acc = layer == 0 || t < T - 1;
-        const int64_t tr = (int64_t)t * p.R + row;
-        const float keep = (row_ok && p.mask && p.mask[tr] == 0) ? 0.f : 1.f;
-        const int nsub = HS / 8;
-        if (has_acc) { mbar_wait(tfull, nuse & 1); tc_fence_after(); ++nuse; }
-#pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-          if (sub < nsub) {
-            float dh[8], g[4][8], cp[8], cc[8], out[4][8];
-            if (has_acc) { tmem_ld8(taddr + sub * 8, dh); tmem_ld_wait(); }
-            else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) dh[e] = 0.f;
-            }
-            const int j = j0 + sub * 8;
-            if (row_ok) {
-#pragma unroll
-              for (int gg = 0; gg < 4; ++gg) ld8g(gates + tr * 4 * H + gg * H + j, g[gg]);
-              ld8g(cst + tr * H + j, cc);
-              if (t > 0) ld8g(cst + (tr - p.R) * H + j, cp);
-              else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) cp[e] = 0.f;
-              }
-              if (t == T - 1) {
-                if (dh_last) { float x[8]; ld8g(dh_last + row * H + j, x);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) dh[e] += x[e]; }
-                if (dc_last) { float x[8]; ld8g(dc_last + row * H + j, x);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) dc[sub * 8 + e] = x[e]; }
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float gi = g[0][e], gf = g[1][e], go = g[2][e], gg_ = g[3][e];
-                const float tcv = ftanh(cc[e]);
-                const float dhe = dh[e] * keep;
-                const float d = (dc[sub * 8 + e] + dhe * go * (1.f - tcv * tcv)) * keep;
-                out[0][e] = d * gg_ * gi * (1.f - gi);
-                out[1][e] = d * cp[e] * gf * (1.f - gf);
-                out[2][e] = dhe * tcv * go * (1.f - go);
-                out[3][e] = d * gi * (1.f - gg_ * gg_);
-                dc[sub * 8 + e] = d * gf;
-              }
-#pragma unroll
-              for (int gg = 0; gg < 4; ++gg) {
-                *reinterpret_cast<uint4*>(da16 + tr * 4 * H + gg * H + j) = ep_pack8(out[gg]);
-                st8g(da + tr * 4 * H + gg * H + j, out[gg]);
-              }
-            }
+          for (int sub = 0; sub < HS / 8; ++sub) {
+            float a[8];
+            tmem_ld8(taddr + sub * 8, a);
+            tmem_ld_wait();
+            if (row_ok) st8g(p.da1 + tr * 4 * H + j0 + sub * 8, a);
           }
-        }
-        if (has_acc) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
+          if (lane == 0) mbar_arrive(sm.tempty);
+          ep_publish(flagX + (size_t)rb * T + t, p.trace, T, t);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          __threadfence();
-          atomicAdd(flag + (size_t)rb * T + t, 1);
+      }
+    } else {
+      // SeqLSTM backward pointwise, dc in registers across the sequence; whole 128-byte lines per thread and access (three passes: o, then
+      // i and g, then f), the fp16 da_t (the operand of the steps that follow) stored ahead of the flag, the fp32 da_t (read after the
+      // kernel by the weight / input gradients) parked in TMEM and stored after it
+      const bool top = role == EP_CELL1;
+      const float* gates = top ? p.gates2 : p.gates1;
+      const float* cst = top ? p.c2 : p.c1;
+      float* da = top ? p.da2 : p.da1;
+      __half* da16 = top ? p.da2_16 : p.da1_16;
+      const float* dh_last = top ? p.dh_last2 : p.dh_last1;
+      const float* dc_last = top ? p.dc_last2 : p.dc_last1;
+      int* flag = top ? flagT : flagB;
+      const uint32_t tstage = taddr + 32;
+      for (int rb = group; rb < p.RB; rb += p.groups) {
+        const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
+        const bool row_ok = row < p.R;
+        float dc[HS];
+        zero32(dc);
+        for (int t = T - 1; t >= 0; --t) {
+          const bool has_acc = t < T - 1;
+          const int64_t tr = (int64_t)t * p.R + row;
+          const float keep = (row_ok && p.mask && p.mask[tr] == 0) ? 0.f : 1.f;
+          const float* grow = gates + tr * 4 * H + j0;
+          float* darow = da + tr * 4 * H + j0;
+          __half* da16row = da16 + tr * 4 * H + j0;
+          float va[HS], vb[HS], dh[HS];
+          // everything the pointwise reads besides the contraction (saved gates, c_t, c_{t-1}, the parked partial) goes to the TMEM staging
+          // columns while the contraction of this step is still running; da_t overwrites the gate columns in place
+          // staging map: S0 = o -> da_o, S1 = c_t, S2 = i -> da_i, S3 = g -> da_g, S4 = f -> da_f, S5 = c_{t-1}, S6 = partial
+          if (!top) wait_flag_generic(flagX + (size_t)rb * T + t, p.nS);     // the parked partial of this step is in place
+          {
+            const float* src[7] = {grow + 2 * H, cst + tr * H + j0, grow, grow + 3 * H, grow + 1 * H,
+                                   t > 0 ? cst + (tr - p.R) * H + j0 : nullptr, top ? nullptr : darow};
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+              if (k == 6 && top) continue;
+              if (row_ok && src[k]) ld32g(src[k], va); else zero32(va);
+              tmem_st32(tstage + k * HS, va);
+            }
+          }
+          tmem_st_wait();
+          if (has_acc) { mbar_wait(sm.tfull, nuse & 1); tc_fence_after(); ++nuse; }
+          if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 4);
+          if (has_acc) tmem_ld32(taddr, dh); else zero32(dh);
+          tmem_ld32(tstage + 0 * HS, va); tmem_ld32(tstage + 1 * HS, vb); tmem_ld_wait();
+          if (has_acc) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sm.tempty);
+          }
+          if (!top) { float pp[HS]; tmem_ld32(tstage + 6 * HS, pp); tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < HS; ++e) dh[e] += pp[e]; }
+          if (t == T - 1 && row_ok) {
+            if (dh_last) { float pp[HS]; ld32g(dh_last + row * H + j0, pp);
+#pragma unroll
+              for (int e = 0; e < HS; ++e) dh[e] += pp[e]; }
+            if (dc_last) ld32g(dc_last + row * H + j0, dc);
+          }
+          // ---- o:  da_o = dh tanh(c) o (1-o);  d = dc + dh o (1 - tanh(c)^2)
+#pragma unroll
+          for (int e = 0; e < HS; ++e) {
+            const float tcv = ftanh(vb[e]), go = va[e], dhe = dh[e] * keep;
+            dc[e] = (dc[e] + dhe * go * (1.f - tcv * tcv)) * keep;           // dc <- d
+            dh[e] = dhe * tcv * go * (1.f - go);
+          }
+          tmem_st32(tstage + 0 * HS, dh);
+          if (row_ok) st32h(da16row + 2 * H, dh);
+          // ---- i, g:  da_i = d g i (1-i);  da_g = d i (1-g^2)
+          tmem_ld32(tstage + 2 * HS, va); tmem_ld32(tstage + 3 * HS, vb); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HS; ++e) dh[e] = dc[e] * vb[e] * va[e] * (1.f - va[e]);
+          tmem_st32(tstage + 2 * HS, dh);
+          if (row_ok) st32h(da16row, dh);
+#pragma unroll
+          for (int e = 0; e < HS; ++e) dh[e] = dc[e] * va[e] * (1.f - vb[e] * vb[e]);
+          tmem_st32(tstage + 3 * HS, dh);
+          if (row_ok) st32h(da16row + 3 * H, dh);
+          // ---- f:  da_f = d c_{t-1} f (1-f);  dc_{t-1} = d f
+          tmem_ld32(tstage + 4 * HS, va); tmem_ld32(tstage + 5 * HS, vb); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HS; ++e) { dh[e] = dc[e] * vb[e] * va[e] * (1.f - va[e]); dc[e] *= va[e]; }
+          tmem_st32(tstage + 4 * HS, dh);
+          if (row_ok) st32h(da16row + 1 * H, dh);
+          ep_publish(flag + (size_t)rb * T + t, p.trace, T, t);
+          // ---- after the flag: fp32 da_t from the staging columns, once this CTA's producer has seen the next step's flag
+          if (t > 0) { mbar_wait(sm.seen, nseen & 1); ++nseen; }
+          tmem_st_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int sg = k == 0 ? 0 : k + 1;                               // staging slot S0, S2, S3, S4
+            const int gate = k == 0 ? 2 : (k == 1 ? 0 : (k == 2 ? 3 : 1));   // = gate o, i, g, f
+            tmem_ld32(tstage + sg * HS, dh); tmem_ld_wait();
+            if (row_ok) st32g(darow + gate * H, dh);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -522,13 +636,71 @@ static CUtensorMap ep_tmap_h(const __half* base, int64_t rows, int64_t cols, int
   return tm;
 }
 
+// VD_ENC_TRACE=1: run the launch with a stamp buffer, then print where a step's time goes (stderr).  Debugging aid, synchronises.
+struct EpTrace {
+  unsigned long long* dev = nullptr;
+  int grid = 0, T = 0;
+  static bool on() { static const bool v = [] { const char* e = getenv("VD_ENC_TRACE"); return e && atoi(e) != 0; }(); return v; }
+  unsigned long long* begin(int grid_, int T_) {
+    if (!on()) return nullptr;
+    grid = grid_; T = T_;
+    VD_CUDA_CHECK(cudaMalloc(&dev, (size_t)grid * T * EP_TRACE_SLOTS * 8));
+    VD_CUDA_CHECK(cudaMemset(dev, 0, (size_t)grid * T * EP_TRACE_SLOTS * 8));
+    return dev;
+  }
+  // role of a CTA = (index in its group) / nS; reverse = BPTT (step t consumes what step t+1 published)
+  void report(cudaStream_t st, const char* name, int nS, bool reverse) {
+    if (!dev) return;
+    VD_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> h((size_t)grid * T * EP_TRACE_SLOTS);
+    VD_CUDA_CHECK(cudaMemcpy(h.data(), dev, h.size() * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dev); dev = nullptr;
+    const int per_group = 3 * nS;
+    auto at = [&](int c, int t, int s) { return h[((size_t)c * T + t) * EP_TRACE_SLOTS + s]; };
+    auto role_of = [&](int c) { return (c % per_group) / nS; };
+    static const char* fwd_names[3] = {"L1 cell", "X2 proj", "L2 cell"};
+    static const char* bwd_names[3] = {"T cell (layer 2)", "X proj", "B cell (layer 1)"};
+    for (int role = 0; role < 3; ++role) {
+      double sum[8] = {0}; int n = 0; double cyc = 0; int ncyc = 0; double prop = 0; int nprop = 0;
+      const int dep = role == EP_PROJ ? EP_CELL1 : role;              // the role whose publish this role's producer waits on
+      for (int c = 0; c < grid; ++c) {
+        if (role_of(c) != role) continue;
+        for (int t = 1; t + 1 < T; ++t) {
+          if (!at(c, t, 0) || !at(c, t, 6)) continue;
+          sum[0] += (double)(at(c, t, 1) - at(c, t, 0));       // flag seen -> last TMA issued
+          sum[1] += (double)(at(c, t, 3) - at(c, t, 0));       // flag seen -> last chunk landed + MMAs issued
+          sum[2] += (double)(at(c, t, 4) - at(c, t, 3));       // -> accumulator ready in the epilogue
+          sum[3] += (double)(at(c, t, 5) - at(c, t, 4));       // epilogue math + stores issued
+          sum[4] += (double)(at(c, t, 6) - at(c, t, 5));       // barrier + fence + atomic
+          sum[5] += (double)((long long)at(c, t, 2) - (long long)at(c, t, 0));   // accumulator free relative to flag seen (<0: no stall)
+          ++n;
+          const int tn = reverse ? t + 1 : t - 1;
+          if (at(c, tn, 6)) { cyc += (double)(at(c, t, 6) - at(c, tn, 6)); ++ncyc; }
+          // flag propagation: my flag seen (wall) minus the latest publish (wall) among the CTAs of the awaited role in my group
+          const int tp = role == EP_PROJ ? t : tn;
+          unsigned long long latest = 0;
+          const int g0 = c / per_group * per_group;
+          for (int o = g0; o < g0 + per_group; ++o)
+            if (role_of(o) == dep && at(o, tp, 7) > latest) latest = at(o, tp, 7);
+          if (latest && at(c, t, 8)) { prop += (double)((long long)at(c, t, 8) - (long long)latest); ++nprop; }
+        }
+      }
+      if (!n) continue;
+      fprintf(stderr, "[enc trace] %s %s: step cycle %.0f clk | flag->TMA issued %.0f | flag->operands landed %.0f | ->acc ready %.0f | "
+              "epilogue %.0f | publish %.0f | acc-free minus flag %.0f | flag propagation %.0f ns  (n=%d)\n",
+              name, (reverse ? bwd_names : fwd_names)[role], ncyc ? cyc / ncyc : 0.0, sum[0] / n, sum[1] / n, sum[2] / n, sum[3] / n,
+              sum[4] / n, sum[5] / n, nprop ? prop / nprop : 0.0, n);
+    }
+  }
+};
+
 }  // namespace tc
 
 bool enc_pair_shape_ok(int64_t R, int H, int sm_count) {
-  return H % 64 == 0 && H <= 512 && R >= 64 && (H / 32 + H / 16) <= sm_count;
+  return H % 64 == 0 && H <= 512 && R >= 64 && 3 * (H / 32) <= sm_count;
 }
 
-// flags: int32 [2 * RB * T] (zeroed here).  gates1 holds the layer-1 x-projection (+ bias) on entry.
+// flags: int32 [3 * RB * T] (zeroed here).  gates1 holds the layer-1 x-projection (+ bias) on entry.
 void enc_pair_forward(LaunchCtx& cx, int T, int64_t R, int H, const __half* W1h16, const __half* W2cat16, const float* bias2,
                       const int32_t* mask, float* gates1, float* c1, float* h1, __half* h1_16, float* gates2, float* c2, float* h2,
                       __half* h2_16, int* flags) {
@@ -536,26 +708,29 @@ void enc_pair_forward(LaunchCtx& cx, int T, int64_t R, int H, const __half* W1h1
   VD_REQUIRE(enc_pair_shape_ok(R, H, cx.sm_count), VD_E_STATE, "enc_pair_forward: shape");
   EncFwdParams p = {};
   p.T = T; p.R = (int)R; p.H = H; p.RB = cdiv(R, 128);
-  p.nS1 = H / 32; p.nS2 = H / 16;
-  p.groups = std::max(1, std::min(p.RB, cx.sm_count / (p.nS1 + p.nS2)));
+  p.nS = H / 32;
+  p.groups = std::max(1, std::min(p.RB, cx.sm_count / (3 * p.nS)));
   p.gates1 = gates1; p.c1 = c1; p.h1 = h1; p.h1_16 = h1_16;
   p.gates2 = gates2; p.c2 = c2; p.h2 = h2; p.h2_16 = h2_16;
   p.bias2 = bias2; p.mask = mask; p.flags = flags;
-  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)2 * p.RB * T * sizeof(int), cx.stream));
+  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)3 * p.RB * T * sizeof(int), cx.stream));
   const int64_t TR = (int64_t)T * R;
   CUtensorMap tH1 = ep_tmap_h(h1_16, TR, H, H, 128), tH2 = ep_tmap_h(h2_16, TR, H, H, 128);
-  CUtensorMap tW1 = ep_tmap_h(W1h16, 4 * (int64_t)H, H, H, 32), tW2 = ep_tmap_h(W2cat16, 4 * (int64_t)H, 2 * (int64_t)H, 2 * (int64_t)H, 16);
+  CUtensorMap tW1 = ep_tmap_h(W1h16, 4 * (int64_t)H, H, H, EP_HS), tW2 = ep_tmap_h(W2cat16, 4 * (int64_t)H, 2 * (int64_t)H, 2 * (int64_t)H, EP_HS);
   static bool attr_set = false;
   if (!attr_set) {
     VD_CUDA_CHECK(cudaFuncSetAttribute(k_enc_pair_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM));
     attr_set = true;
   }
-  k_enc_pair_fwd<<<p.groups * (p.nS1 + p.nS2), EP_THREADS, EP_SMEM, cx.stream>>>(tH1, tH2, tW1, tW2, p);
+  EpTrace trace;
+  p.trace = trace.begin(p.groups * 3 * p.nS, T);
+  k_enc_pair_fwd<<<p.groups * 3 * p.nS, EP_THREADS, EP_SMEM, cx.stream>>>(tH1, tH2, tW1, tW2, p);
   check_launch(cx, "k_enc_pair_fwd");
+  trace.report(cx.stream, "fwd", p.nS, false);
 }
 
 
-// gates*/c* = the activations the forward saved; da*/da*_16 out (all T steps); flags int32 [2 * RB * T]
+// gates*/c* = the activations the forward saved; da*/da*_16 out (all T steps); flags int32 [3 * RB * T]
 void enc_pair_backward(LaunchCtx& cx, int T, int64_t R, int H, const __half* B1cat16, const __half* Whb2_16, const int32_t* mask,
                        const float* gates1, const float* c1, const float* gates2, const float* c2, const float* dh_last1,
                        const float* dc_last1, const float* dh_last2, const float* dc_last2, float* da1, __half* da1_16, float* da2,
@@ -564,24 +739,27 @@ void enc_pair_backward(LaunchCtx& cx, int T, int64_t R, int H, const __half* B1c
   VD_REQUIRE(enc_pair_shape_ok(R, H, cx.sm_count), VD_E_STATE, "enc_pair_backward: shape");
   EncBwdParams p = {};
   p.T = T; p.R = (int)R; p.H = H; p.RB = cdiv(R, 128);
-  p.nS1 = H / 16; p.nS2 = H / 32;
-  p.groups = std::max(1, std::min(p.RB, cx.sm_count / (p.nS1 + p.nS2)));
+  p.nS = H / 32;
+  p.groups = std::max(1, std::min(p.RB, cx.sm_count / (3 * p.nS)));
   p.gates1 = gates1; p.c1 = c1; p.da1 = da1; p.da1_16 = da1_16;
   p.gates2 = gates2; p.c2 = c2; p.da2 = da2; p.da2_16 = da2_16;
   p.dh_last1 = dh_last1; p.dc_last1 = dc_last1; p.dh_last2 = dh_last2; p.dc_last2 = dc_last2;
   p.mask = mask; p.flags = flags;
-  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)2 * p.RB * T * sizeof(int), cx.stream));
+  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)3 * p.RB * T * sizeof(int), cx.stream));
   const int64_t TR = (int64_t)T * R;
   const int64_t G = 4 * (int64_t)H;
   CUtensorMap tA1 = ep_tmap_h(da1_16, TR, G, G, 128), tA2 = ep_tmap_h(da2_16, TR, G, G, 128);
-  CUtensorMap tW1 = ep_tmap_h(B1cat16, H, 2 * G, 2 * G, 16), tW2 = ep_tmap_h(Whb2_16, H, G, G, 32);
+  CUtensorMap tW1 = ep_tmap_h(B1cat16, H, 2 * G, 2 * G, EP_HS), tW2 = ep_tmap_h(Whb2_16, H, G, G, EP_HS);
   static bool attr_set = false;
   if (!attr_set) {
     VD_CUDA_CHECK(cudaFuncSetAttribute(k_enc_pair_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM));
     attr_set = true;
   }
-  k_enc_pair_bwd<<<p.groups * (p.nS1 + p.nS2), EP_THREADS, EP_SMEM, cx.stream>>>(tA1, tA2, tW1, tW2, p);
+  EpTrace trace;
+  p.trace = trace.begin(p.groups * 3 * p.nS, T);
+  k_enc_pair_bwd<<<p.groups * 3 * p.nS, EP_THREADS, EP_SMEM, cx.stream>>>(tA1, tA2, tW1, tW2, p);
   check_launch(cx, "k_enc_pair_bwd");
+  trace.report(cx.stream, "bwd", p.nS, true);
 }
 
 }  // namespace vd

@@ -536,7 +536,7 @@ void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaSt
     __half* W2c = arena.get<__half>((int64_t)G * 2 * H);
     cvt_f32_to_f16(cx, W1h, H, Wtp(l1.wseg) + l1.D, l1.D + H, G, H);                   // [4H, H]   recurrent block of layer 1
     cvt_f32_to_f16(cx, W2c, 2 * H, Wtp(l2.wseg), 2 * H, G, 2 * H);                     // [4H, 2H]  [Wx2 | Wh2] of layer 2
-    int* flags = arena.get<int>(2 * (int64_t)cdiv(R, 128) * T);
+    int* flags = arena.get<int>(3 * (int64_t)cdiv(R, 128) * T);
     LaunchCtx::Scope sc2(&cx, "enc_pair_fwd", 2.0 * T * R * G * 3.0 * H, 4.0 * T * R * (2.0 * G + 2.0 * G + 6.0 * H));
     enc_pair_forward(cx, T, R, H, W1h, W2c, Wp(l2.wseg + 1), l1.mask, l1.gates, l1.c, l1.h, l1.h16, l2.gates, l2.c, l2.h, l2.h16, flags);
     return;
@@ -725,7 +725,7 @@ void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2,
     cvt_f32_to_f16(cx, Whb2, G, Wp(l2.wseg) + (int64_t)l2.D * G, G, H, G);                 // Wh2: rows D2.. of (D2+H, 4H)
     cvt_f32_to_f16(cx, B1cat, 2 * G, Wp(l2.wseg), G, H, G);                                 // [Wx2 | ...]: rows 0..H-1 of layer 2
     cvt_f32_to_f16(cx, B1cat + G, 2 * G, Wp(l1.wseg) + (int64_t)l1.D * G, G, H, G);         // [... | Wh1]
-    int* flags = arena.get<int>(2 * (int64_t)cdiv(R, 128) * T);
+    int* flags = arena.get<int>(3 * (int64_t)cdiv(R, 128) * T);
     {
       LaunchCtx::Scope sc2(&cx, "enc_pair_bwd", 2.0 * T * R * (double)H * 3.0 * G, 4.0 * T * R * (4.0 * G + 4.0 * H));
       enc_pair_backward(cx, T, R, H, B1cat, Whb2, l1.mask, l1.gates, l1.c, l2.gates, l2.c, dh_last1, dc_last1, dh_last2, dc_last2,

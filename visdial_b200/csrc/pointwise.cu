@@ -277,7 +277,38 @@ __global__ void k_vocab_lse_finish(const float* __restrict__ pm, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int CS_ROWS = 1024;
+// out[c] += sum_r X[r, c] (bias gradients).  HBM-bound: a block covers 256 rows x 128 columns, a warp reads whole 512-byte row pieces
+// (float4 per lane) of every 8th row with 4 loads in flight, the 8 warps are combined in shared memory, then one atomicAdd per column.
+constexpr int CS_ROWS = 256;
+__global__ void __launch_bounds__(256) k_colsum_add4(float* __restrict__ out, const float* __restrict__ X, int64_t rows, int cols, int64_t ldx) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + lane) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+    const float* p = X + c;
+    int64_t r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = *reinterpret_cast<const float4*>(p + r * ldx), b = *reinterpret_cast<const float4*>(p + (r + 8) * ldx);
+      const float4 d = *reinterpret_cast<const float4*>(p + (r + 16) * ldx), e = *reinterpret_cast<const float4*>(p + (r + 24) * ldx);
+      acc.x += (a.x + b.x) + (d.x + e.x); acc.y += (a.y + b.y) + (d.y + e.y);
+      acc.z += (a.z + b.z) + (d.z + e.z); acc.w += (a.w + b.w) + (d.w + e.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = *reinterpret_cast<const float4*>(p + r * ldx);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { const float4 o = red[w][lane]; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    atomicAdd(out + c, acc.x); atomicAdd(out + c + 1, acc.y); atomicAdd(out + c + 2, acc.z); atomicAdd(out + c + 3, acc.w);
+  }
+}
+// any shape (odd column counts, unaligned leading dimension): one thread per column
 __global__ void k_colsum_add(float* __restrict__ out, const float* __restrict__ X, int64_t rows, int cols, int64_t ldx) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
@@ -950,7 +981,8 @@ void lstm_pointwise_bwd(LaunchCtx& cx, const float* gates, const float* c_prev, 
 void colsum_add(LaunchCtx& cx, float* out, const float* X, int64_t rows, int cols, int64_t ldx) {
   if (rows <= 0 || cols <= 0) return;
   dim3 grid(cdiv(cols, 128), cdiv(rows, CS_ROWS));
-  k_colsum_add<<<grid, 128, 0, cx.stream>>>(out, X, rows, cols, ldx);
+  if (cols % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0) k_colsum_add4<<<grid, 256, 0, cx.stream>>>(out, X, rows, cols, ldx);
+  else k_colsum_add<<<grid, 128, 0, cx.stream>>>(out, X, rows, cols, ldx);
   check_launch(cx, "colsum_add");
 }
 void dropout_apply(LaunchCtx& cx, float* out, const float* in, int64_t n, DropCfg d, uint32_t site) {
