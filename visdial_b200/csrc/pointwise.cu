@@ -585,6 +585,11 @@ __global__ void k_san_expand_dropout(float* __restrict__ img_tr, const float* __
   reinterpret_cast<float4*>(img_tr)[i] = v;
 }
 
+// tanh for the two score kernels (65 M evaluations per pass at the benched size): exp-based, absolute error ~1e-7
+__device__ __forceinline__ float tanh_e(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 // warp per (n,p)
 __global__ void k_san_score_fwd(const float* __restrict__ ic, const float* __restrict__ qc, const float* __restrict__ w,
                                 const float* __restrict__ b, float* __restrict__ s, int64_t NP, int P, int Cm, DropCfg d, uint32_t site) {
@@ -599,18 +604,23 @@ __global__ void k_san_score_fwd(const float* __restrict__ ic, const float* __res
     float4 ww = reinterpret_cast<const float4*>(w)[c4];
     float f[4];
     drop_factor4(d, site, (uint64_t)(row * (Cm >> 2) + c4), f);
-    acc += ww.x * f[0] * tanhf(a.x + q.x) + ww.y * f[1] * tanhf(a.y + q.y) + ww.z * f[2] * tanhf(a.z + q.z) +
-           ww.w * f[3] * tanhf(a.w + q.w);
+    acc += ww.x * f[0] * tanh_e(a.x + q.x) + ww.y * f[1] * tanh_e(a.y + q.y) + ww.z * f[2] * tanh_e(a.z + q.z) +
+           ww.w * f[3] * tanh_e(a.w + q.w);
   }
   acc = warp_sum(acc);
   if (l == 0) s[row] = acc + b[0];
 }
 
-// block per n
-__global__ void k_san_softmax_att_fwd(const float* __restrict__ s, float* __restrict__ p, const float* __restrict__ img_tr,
-                                      const float* __restrict__ u_in, float* __restrict__ u_out, int P, int H) {
-  extern __shared__ float sm[];          // P floats + 33
+// The four kernels below stream (N, P, H) / (N, P, Cm) tensors (128 MB each at the benched size) once: they are HBM-bound, so every
+// thread moves float4 pieces, keeps 4 independent loads in flight, and a dialog round's work is spread over several blocks.
+
+// grid (N, 2 halves of H), block 256: softmax over the P scores (recomputed per half: P is 196), then u_out = p . img_tr + u_in for the
+// half's columns — thread = float4 column piece x position group, groups combined in shared memory
+__global__ void __launch_bounds__(256) k_san_softmax_att_fwd(const float* __restrict__ s, float* __restrict__ p, const float* __restrict__ img_tr,
+                                                             const float* __restrict__ u_in, float* __restrict__ u_out, int P, int H) {
+  extern __shared__ float sm[];          // P floats + 33 + 256 float4
   float* sp = sm; float* red = sm + P;
+  float4* part = reinterpret_cast<float4*>(sm + ((P + 33 + 3) & ~3));
   const int64_t n = blockIdx.x;
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < P; i += blockDim.x) { float v = s[n * P + i]; sp[i] = v; mx = fmaxf(mx, v); }
@@ -618,30 +628,58 @@ __global__ void k_san_softmax_att_fwd(const float* __restrict__ s, float* __rest
   float sum = 0.f;
   for (int i = threadIdx.x; i < P; i += blockDim.x) { float e = expf(sp[i] - mx); sp[i] = e; sum += e; }
   sum = block_sum(sum, red);
-  for (int i = threadIdx.x; i < P; i += blockDim.x) { float v = sp[i] / sum; sp[i] = v; p[n * P + i] = v; }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { float v = sp[i] / sum; sp[i] = v; if (blockIdx.y == 0) p[n * P + i] = v; }
   __syncthreads();
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float acc = 0.f;
-    const float* base = img_tr + n * P * H + c;
-    for (int i = 0; i < P; ++i) acc += sp[i] * base[(int64_t)i * H];
-    u_out[n * H + c] = acc + u_in[n * H + c];
+  const int H4 = H >> 2, half = (H4 + 1) >> 1;
+  const int c_lo = blockIdx.y * half, c_hi = min(H4, c_lo + half);
+  const int tpc = min(half, (int)blockDim.x), npg = blockDim.x / tpc;
+  const int tc = threadIdx.x % tpc, pg = threadIdx.x / tpc;
+  const float4* base = reinterpret_cast<const float4*>(img_tr) + n * P * H4;
+  for (int c0 = c_lo; c0 < c_hi; c0 += tpc) {
+    const int c4 = c0 + tc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pg < npg && c4 < c_hi) {
+      int i = pg;
+      for (; i + 3 * npg < P; i += 4 * npg) {
+        const float4 a = base[(int64_t)i * H4 + c4], b = base[(int64_t)(i + npg) * H4 + c4];
+        const float4 c = base[(int64_t)(i + 2 * npg) * H4 + c4], e = base[(int64_t)(i + 3 * npg) * H4 + c4];
+        const float w0 = sp[i], w1 = sp[i + npg], w2 = sp[i + 2 * npg], w3 = sp[i + 3 * npg];
+        acc.x += w0 * a.x + w1 * b.x + w2 * c.x + w3 * e.x; acc.y += w0 * a.y + w1 * b.y + w2 * c.y + w3 * e.y;
+        acc.z += w0 * a.z + w1 * b.z + w2 * c.z + w3 * e.z; acc.w += w0 * a.w + w1 * b.w + w2 * c.w + w3 * e.w;
+      }
+      for (; i < P; i += npg) {
+        const float4 a = base[(int64_t)i * H4 + c4]; const float w0 = sp[i];
+        acc.x += w0 * a.x; acc.y += w0 * a.y; acc.z += w0 * a.z; acc.w += w0 * a.w;
+      }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (pg == 0 && c4 < c_hi) {
+      for (int g = 1; g < npg; ++g) { const float4 o = part[g * tpc + tc]; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+      const float4 u = reinterpret_cast<const float4*>(u_in)[n * H4 + c4];
+      reinterpret_cast<float4*>(u_out)[n * H4 + c4] = make_float4(acc.x + u.x, acc.y + u.y, acc.z + u.z, acc.w + u.w);
+    }
+    __syncthreads();
   }
 }
 
-// block per n: dp = du . img_tr ; ds = p*(dp - sum p dp) ; dimg_tr = p * du
-__global__ void k_san_att_bwd(const float* __restrict__ du, const float* __restrict__ p, const float* __restrict__ img_tr,
-                              float* __restrict__ ds, float* __restrict__ dimg_tr, int P, int H) {
+// block per n (512 threads): dp = du . img_tr ; ds = p*(dp - sum p dp) ; dimg_tr = p * du
+__global__ void __launch_bounds__(512) k_san_att_bwd(const float* __restrict__ du, const float* __restrict__ p, const float* __restrict__ img_tr,
+                                                     float* __restrict__ ds, float* __restrict__ dimg_tr, int P, int H) {
   extern __shared__ float sm[];          // H + P + P + 33
   float* sdu = sm; float* sp = sdu + H; float* sdp = sp + P; float* red = sdp + P;
   const int64_t n = blockIdx.x;
   const int tid = threadIdx.x, nw = blockDim.x >> 5, w = tid >> 5, l = tid & 31;
+  const int H4 = H >> 2;
   for (int c = tid; c < H; c += blockDim.x) sdu[c] = du[n * H + c];
   for (int i = tid; i < P; i += blockDim.x) sp[i] = p[n * P + i];
   __syncthreads();
+  const float4* sdu4 = reinterpret_cast<const float4*>(sdu);
   for (int i = w; i < P; i += nw) {
-    const float* row = img_tr + (n * P + i) * H;
+    const float4* row = reinterpret_cast<const float4*>(img_tr) + (n * P + i) * H4;
     float acc = 0.f;
-    for (int c = l; c < H; c += 32) acc += sdu[c] * row[c];
+#pragma unroll 4
+    for (int c = l; c < H4; c += 32) { const float4 a = row[c], b = sdu4[c]; acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
     acc = warp_sum(acc);
     if (l == 0) sdp[i] = acc;
   }
@@ -650,54 +688,90 @@ __global__ void k_san_att_bwd(const float* __restrict__ du, const float* __restr
   for (int i = tid; i < P; i += blockDim.x) part += sp[i] * sdp[i];
   float dot = block_sum(part, red);
   for (int i = tid; i < P; i += blockDim.x) ds[n * P + i] = sp[i] * (sdp[i] - dot);
-  for (int64_t o = tid; o < (int64_t)P * H; o += blockDim.x) {
-    int i = (int)(o / H), c = (int)(o % H);
-    dimg_tr[n * P * H + o] = sp[i] * sdu[c];
+  float4* out = reinterpret_cast<float4*>(dimg_tr) + n * P * H4;
+  for (int i = w; i < P; i += nw) {
+    const float pi = sp[i];
+    for (int c = l; c < H4; c += 32) { const float4 b = sdu4[c]; out[(int64_t)i * H4 + c] = make_float4(pi * b.x, pi * b.y, pi * b.z, pi * b.w); }
   }
 }
 
-// block per n, threads over c; loop p.  Recomputes y = tanh(ic + qc) and the dropout factor.
-__global__ void k_san_score_bwd(const float* __restrict__ ds, const float* __restrict__ ic, const float* __restrict__ qc,
-                                const float* __restrict__ w, float* __restrict__ dic, float* __restrict__ dqc,
-                                float* __restrict__ dw, float* __restrict__ db, int P, int Cm, DropCfg d, uint32_t site) {
-  extern __shared__ float sm[];          // P floats
+// grid (N, column slices), block 256: thread = float4 column piece x position group; a block walks ALL P positions of its columns, the
+// position groups are combined in shared memory in a fixed order, so dqc — an intermediate gradient that flows on into the encoder — is
+// written once and deterministically (only the leaf gradients dw, db use atomics).  Recomputes y = tanh(ic + qc) and the dropout factor.
+__global__ void __launch_bounds__(256) k_san_score_bwd(const float* __restrict__ ds, const float* __restrict__ ic, const float* __restrict__ qc,
+                                                       const float* __restrict__ w, float* __restrict__ dic, float* __restrict__ dqc,
+                                                       float* __restrict__ dw, float* __restrict__ db, int P, int Cm, DropCfg d, uint32_t site) {
+  extern __shared__ float sm[];          // P floats (ds row), then 2 x 256 float4
+  float4* part_q = reinterpret_cast<float4*>(sm + ((P + 3) & ~3));
+  float4* part_w = part_q + 256;
   const int64_t n = blockIdx.x;
   for (int i = threadIdx.x; i < P; i += blockDim.x) sm[i] = ds[n * P + i];
   __syncthreads();
-  for (int c = threadIdx.x; c < Cm; c += blockDim.x) {
-    float q = qc[n * Cm + c], wc = w[c], aq = 0.f, aw = 0.f;
-    for (int i = 0; i < P; ++i) {
-      int64_t idx = (n * P + i) * Cm + c;
-      float y = tanhf(ic[idx] + q);
-      float f = drop_factor(d, site, (uint64_t)idx);
-      float g = sm[i] * f;
-      float dpre = g * wc * (1.f - y * y);
-      dic[idx] = dpre;
-      aq += dpre;
-      aw += g * y;
+  const int C4 = Cm >> 2, per = (C4 + gridDim.y - 1) / gridDim.y;
+  const int c_lo = blockIdx.y * per, c_hi = min(C4, c_lo + per);
+  const int tpc = max(1, min(per, (int)blockDim.x)), npg = blockDim.x / tpc;
+  const int tc = threadIdx.x % tpc, pg = threadIdx.x / tpc;
+  const float4* ic4 = reinterpret_cast<const float4*>(ic);
+  float4* dic4 = reinterpret_cast<float4*>(dic);
+  for (int c0 = c_lo; c0 < c_hi; c0 += tpc) {
+    const int c4 = c0 + tc;
+    float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), aw = aq;
+    if (pg < npg && c4 < c_hi) {
+      const float4 q = reinterpret_cast<const float4*>(qc)[n * C4 + c4], wc = reinterpret_cast<const float4*>(w)[c4];
+#pragma unroll 4
+      for (int i = pg; i < P; i += npg) {
+        const int64_t idx4 = (n * P + i) * C4 + c4;
+        const float4 a = ic4[idx4];
+        float f[4];
+        drop_factor4(d, site, (uint64_t)idx4, f);
+        const float g = sm[i];
+        const float y0 = tanh_e(a.x + q.x), y1 = tanh_e(a.y + q.y), y2 = tanh_e(a.z + q.z), y3 = tanh_e(a.w + q.w);
+        const float g0 = g * f[0], g1 = g * f[1], g2 = g * f[2], g3 = g * f[3];
+        const float4 o = make_float4(g0 * wc.x * (1.f - y0 * y0), g1 * wc.y * (1.f - y1 * y1), g2 * wc.z * (1.f - y2 * y2), g3 * wc.w * (1.f - y3 * y3));
+        dic4[idx4] = o;
+        aq.x += o.x; aq.y += o.y; aq.z += o.z; aq.w += o.w;
+        aw.x += g0 * y0; aw.y += g1 * y1; aw.z += g2 * y2; aw.w += g3 * y3;
+      }
     }
-    dqc[n * Cm + c] = aq;
-    atomicAdd(dw + c, aw);
+    part_q[threadIdx.x] = aq; part_w[threadIdx.x] = aw;
+    __syncthreads();
+    if (pg == 0 && c4 < c_hi) {
+      for (int g = 1; g < npg; ++g) {
+        const float4 oq = part_q[g * tpc + tc], ow = part_w[g * tpc + tc];
+        aq.x += oq.x; aq.y += oq.y; aq.z += oq.z; aq.w += oq.w;
+        aw.x += ow.x; aw.y += ow.y; aw.z += ow.z; aw.w += ow.w;
+      }
+      reinterpret_cast<float4*>(dqc)[n * C4 + c4] = aq;
+      atomicAdd(dw + 4 * c4, aw.x); atomicAdd(dw + 4 * c4 + 1, aw.y); atomicAdd(dw + 4 * c4 + 2, aw.z); atomicAdd(dw + 4 * c4 + 3, aw.w);
+    }
+    __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  // db: the scores of a row enter a softmax, so sum_i ds[n, i] is zero up to rounding — summed in a fixed order by one thread
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
     float acc = 0.f;
     for (int i = 0; i < P; ++i) acc += sm[i];
     atomicAdd(db, acc);
   }
 }
 
+// thread = float4 of (B,P,H): sum over the R rounds that share the image (dropout factor recomputed), times tanh'
 __global__ void k_san_collapse_bwd(const float* __restrict__ dimg_tr, const float* __restrict__ t, float* __restrict__ dt_pre,
-                                   int64_t total, int R, int64_t PH, DropCfg d, uint32_t site) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // index into (B,P,H)
-  if (i >= total) return;
-  int64_t b = i / PH, rem = i % PH;
-  float acc = 0.f;
+                                   int64_t total4, int R, int64_t PH4, DropCfg d, uint32_t site) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // float4 index into (B,P,H)
+  if (i >= total4) return;
+  int64_t b = i / PH4, rem = i % PH4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
   for (int r = 0; r < R; ++r) {
-    int64_t idx = (b * R + r) * PH + rem;
-    acc += dimg_tr[idx] * drop_factor(d, site, (uint64_t)idx);
+    const int64_t idx4 = (b * R + r) * PH4 + rem;
+    const float4 v = reinterpret_cast<const float4*>(dimg_tr)[idx4];
+    float f[4];
+    drop_factor4(d, site, (uint64_t)idx4, f);
+    acc.x += v.x * f[0]; acc.y += v.y * f[1]; acc.z += v.z * f[2]; acc.w += v.w * f[3];
   }
-  float tv = t[i];
-  dt_pre[i] = acc * (1.f - tv * tv);
+  const float4 tv = reinterpret_cast<const float4*>(t)[i];
+  reinterpret_cast<float4*>(dt_pre)[i] = make_float4(acc.x * (1.f - tv.x * tv.x), acc.y * (1.f - tv.y * tv.y), acc.z * (1.f - tv.z * tv.z),
+                                                     acc.w * (1.f - tv.w * tv.w));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1068,29 +1142,35 @@ void san_score_fwd(LaunchCtx& cx, const float* img_common, const float* ques_com
 void san_softmax_att_fwd(LaunchCtx& cx, const float* s, float* p, const float* img_tr, const float* u_in, float* u_out,
                          int64_t N, int P, int H) {
   if (N <= 0) return;
-  size_t smem = (size_t)(P + 33) * sizeof(float);
-  k_san_softmax_att_fwd<<<(int)N, 256, smem, cx.stream>>>(s, p, img_tr, u_in, u_out, P, H);
+  VD_REQUIRE(H % 4 == 0, -1, "H % 4");
+  size_t smem = (size_t)(((P + 33 + 3) & ~3) + 256 * 4) * sizeof(float);
+  k_san_softmax_att_fwd<<<dim3((unsigned)N, 2), 256, smem, cx.stream>>>(s, p, img_tr, u_in, u_out, P, H);
   check_launch(cx, "san_softmax_att_fwd");
 }
 void san_att_bwd(LaunchCtx& cx, const float* du, const float* p, const float* img_tr, float* ds, float* dimg_tr, int64_t N,
                  int P, int H) {
   if (N <= 0) return;
+  VD_REQUIRE(H % 4 == 0, -1, "H % 4");
   size_t smem = (size_t)(H + 2 * P + 33) * sizeof(float);
-  k_san_att_bwd<<<(int)N, 256, smem, cx.stream>>>(du, p, img_tr, ds, dimg_tr, P, H);
+  k_san_att_bwd<<<(int)N, 512, smem, cx.stream>>>(du, p, img_tr, ds, dimg_tr, P, H);
   check_launch(cx, "san_att_bwd");
 }
 void san_score_bwd(LaunchCtx& cx, const float* ds, const float* img_common, const float* ques_common, const float* w,
                    float* d_img_common, float* d_ques_common, float* dw, float* db, int64_t N, int P, int Cm, DropCfg d,
                    uint32_t site) {
   if (N <= 0) return;
-  k_san_score_bwd<<<(int)N, 256, P * sizeof(float), cx.stream>>>(ds, img_common, ques_common, w, d_img_common,
-                                                                 d_ques_common, dw, db, P, Cm, d, site);
+  VD_REQUIRE(Cm % 4 == 0, -1, "commonEmbeddingSize % 4");
+  const int CS = Cm >= 512 ? 4 : 1;                      // column slices per dialog round
+  const size_t smem = (size_t)(((P + 3) & ~3) + 2 * 256 * 4) * sizeof(float);
+  k_san_score_bwd<<<dim3((unsigned)N, CS), 256, smem, cx.stream>>>(ds, img_common, ques_common, w, d_img_common, d_ques_common, dw, db, P,
+                                                                    Cm, d, site);
   check_launch(cx, "san_score_bwd");
 }
 void san_collapse_bwd(LaunchCtx& cx, const float* dimg_tr, const float* t, float* dt_pre, int B, int R, int P, int H,
                       DropCfg d, uint32_t site) {
-  int64_t PH = (int64_t)P * H, total = (int64_t)B * PH;
-  L1D(k_san_collapse_bwd, total, dimg_tr, t, dt_pre, total, R, PH, d, site);
+  VD_REQUIRE(H % 4 == 0, -1, "H % 4");
+  int64_t PH4 = (int64_t)P * H / 4, total4 = (int64_t)B * PH4;
+  L1D(k_san_collapse_bwd, total4, dimg_tr, t, dt_pre, total4, R, PH4, d, site);
 }
 
 void disc_scores_fwd(LaunchCtx& cx, const float* feat, const float* encOut, float* scores, int64_t N, int K, int H) {
