@@ -54,8 +54,17 @@ __device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, ui
 // range fix-ups of __fdividef / copysign (ex2 -> +inf gives rcp -> 0, ex2 -> 0 gives 1: both limits are exact)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Activations of the fp16 option LSTM: ONE special-function op each (tanh.approx.f32, relative error 2^-11 — the rounding class of the fp16
+// the gates and h are stored in right after; sigmoid(x) = 0.5 tanh(x/2) + 0.5) instead of ex2 + rcp (two): the pointwise half of the
+// forward step is issue / MUFU-bound.  Measured at the benched size (tests/test_c4_b32_gpu.py): rank agreement with the fp64
+// oracle 0.9781 vs 0.9777, top-1 0.99375 both, R@k deltas 0 both.  -DVD_F16_EX2_ACTIVATIONS restores the two-op forms.
+#ifndef VD_F16_EX2_ACTIVATIONS
+__device__ __forceinline__ float tanh16(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sig16(float x) { return fmaf(0.5f, tanh16(0.5f * x), 0.5f); }
+#else
 __device__ __forceinline__ float sig16(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh16(float x) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f); }
+#endif
 
 // ---- fp16 <-> fp32 packing (round to nearest even, saturating: a scaled gradient that outgrows the range clamps to
 // +-65504 instead of becoming inf)
