@@ -26,7 +26,11 @@ _I32_KEYS = ("ques", "ques_length", "ans", "ans_length", "cap", "cap_length", "o
 
 class DeviceBatch(Batch):
     """A batch table whose tensors are device buffers owned by the corpus (vd_batch.on_device = 1).  `batch[key]` reads
-    the tensor back to the host (tests, display); the engine consumes the device pointers directly."""
+    the tensor back to the host (tests, display); the engine consumes the device pointers directly.
+
+    LIFETIME: the corpus assembles batches into a two-slot ring of device buffers (csrc/corpus.cu), so a DeviceBatch is valid until the
+    SECOND later `getTrainBatch` / `getTestBatch` call on the same dataloader — enough to prepare batch i+1 while the engine consumes batch i.
+    Keep a host copy (`batch[key]`) of anything needed longer."""
 
     _SHAPES = {
         "ques_fwd": lambda b, R, K: (b.B, R, b.Tq), "hist": lambda b, R, K: (b.B, R, b.Th),
