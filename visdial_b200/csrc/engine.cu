@@ -532,6 +532,7 @@ void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaSt
     lstm_forward_begin(l2, true);
     l1.h16 = arena.get<__half>((int64_t)T * R * H);
     l2.h16 = arena.get<__half>((int64_t)T * R * H);
+    l2.x16 = l1.h16;
     __half* W1h = arena.get<__half>((int64_t)G * H);
     __half* W2c = arena.get<__half>((int64_t)G * 2 * H);
     cvt_f32_to_f16(cx, W1h, H, Wtp(l1.wseg) + l1.D, l1.D + H, G, H);                   // [4H, H]   recurrent block of layer 1
@@ -661,12 +662,20 @@ void Engine::lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float*
   float* dWs = dWp(r.wseg);
   const float* A = r.x ? r.x : Wp(0);
   const int64_t lda = r.x ? D : cfg.E;
+  const bool pair16 = !r.f16 && r.h16 && r.da16 && H % 64 == 0 && TR - R >= 256;
   if (r.f16) {
     if (r.T > 1) {
       LaunchCtx::Scope sc(&cx, "gemm_wgrad", 2.0 * H * G * (double)(TR - R), 2.0 * (double)(TR - R) * (H + G));
       gemm_atb16(cx, H, G, TR - R, r.h16, H, r.da16 + R * G, G, dWs + (int64_t)D * G, G, r.scale2 + 1);
     }
-  } else if (r.T > 1) gemm_atb(H, G, TR - R, r.h, H, nullptr, da + R * G, G, dWs + (int64_t)D * G, G);
+  } else if (r.T > 1) {
+    // persistent pair (enc_lstm.cu): its kernels left fp16 copies of h and da — the operands of the recurrence itself — so the weight
+    // gradients contract those on the fp16 tensor-core path (fp32 accumulation) instead of the TF32 one
+    if (pair16) {
+      LaunchCtx::Scope sc(&cx, "gemm_wgrad", 2.0 * H * G * (double)(TR - R), 2.0 * (double)(TR - R) * (H + G));
+      gemm_atb16(cx, H, G, TR - R, r.h16, H, r.da16 + R * G, G, dWs + (int64_t)D * G, G, nullptr);
+    } else gemm_atb(H, G, TR - R, r.h, H, nullptr, da + R * G, G, dWs + (int64_t)D * G, G);
+  }
   if (r.h0) gemm_atb(H, G, R, r.h0, H, nullptr, da, G, dWs + (int64_t)D * G, G);
   if (!r.x && tcmode()) {
     // Embedding-gathered input: every x_t is a row of the (V+1, E) table, so the three x-side gradients collapse
@@ -693,7 +702,10 @@ void Engine::lstm_backward_end(LstmRun& r, float* dx_out, float* dh0_out, float*
     VD_REQUIRE(dx_out == nullptr, VD_E_STATE, "projected-space embedding gradient: caller must not ask for dx");
     return;
   }
-  gemm_atb(D, G, TR, A, lda, r.gather, da, G, dWs, G);
+  if (pair16 && r.x16 && !r.gather && D % 64 == 0) {
+    LaunchCtx::Scope sc(&cx, "gemm_wgrad", 2.0 * D * G * (double)TR, 2.0 * (double)TR * (D + G));
+    gemm_atb16(cx, D, G, TR, r.x16, D, r.da16, G, dWs, G, nullptr);
+  } else gemm_atb(D, G, TR, A, lda, r.gather, da, G, dWs, G);
   colsum_add(cx, dWp(r.wseg + 1), da, TR, G, G);
   if (dx_out) gemm_tn((int)TR, D, G, da, G, nullptr, Ws, G, dx_out, D, 0.f, nullptr, 0);
 }

@@ -78,6 +78,7 @@ struct LstmRun {
   // VD_MATH_F16 run state (lstm16.cu): fp16 h / activated gates / da and x-projection table, fp32 c; `h` and `gates` stay null
   bool f16 = false;
   __half *h16 = nullptr, *gates16 = nullptr, *da16 = nullptr, *P16 = nullptr, *Wh16 = nullptr, *Whb16 = nullptr;
+  const __half* x16 = nullptr;       // fp16 copy of x when a persistent pair produced one (layer 2: the h1 sequence)
   float* h32_last = nullptr;         // fp32 copy of the last step's h (what the fp32 consumers of the run read)
   float* scale2 = nullptr;           // device {s, 1/s}: power-of-two scale of the BPTT (chosen from max|dL/dh_T|)
   const float* h_last() const { return f16 ? h32_last : h + (int64_t)(saved ? T - 1 : (T - 1) & 1) * R * H; }
