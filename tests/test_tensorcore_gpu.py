@@ -395,3 +395,31 @@ def test_fused_vocab_gen_retrieval_ranks():
     assert np.array_equal(got[VD_MATH_FP32], ref)
     assert (got[VD_MATH_TF32] == ref).mean() > 0.9
     assert np.array_equal(np.sort(got[VD_MATH_TF32], 1), np.sort(ref, 1))
+
+
+@pytest.mark.parametrize("enc", ["mn-att-ques-im-hist", "hrea-ques-im-hist"])
+def test_persistent_encoder_walks_several_row_blocks(enc):
+    """52 dialogs = 520 encoder rows = 5 row blocks of 128 (the last one partial) on the 3 CTA groups of the persistent encoder LSTM
+    kernels (enc_lstm.cu): every CTA walks several row blocks in turn, with its barrier phases, flag counters and register state carried
+    across them.  F16 mode against the engine's own fp32 mode on one training step (dropout on), loss and per-segment gradients."""
+    p = full_params(enc, "disc")
+    flat = init_parameters(p, seed=5)
+    nb = make_batch(p, 52, seed=9)
+    out = {}
+    for mode in (VD_MATH_FP32, VD_MATH_F16):
+        eng = Engine(p)
+        eng.set_math_mode(mode)
+        eng.set_parameters(flat)
+        eng.set_training(1)
+        eng.set_dropout_seed(3, 1)
+        eng.zero_grad()
+        loss = eng.forward_backward(Batch(nb))
+        out[mode] = (loss, eng.get_gradients().astype(np.float64))
+        eng.close()
+    (l0, g0), (l1, g1) = out[VD_MATH_FP32], out[VD_MATH_F16]
+    assert abs(l1 - l0) < 5e-3 * abs(l0), (l0, l1)
+    for name, s in seg_slices(p).items():
+        m = float(np.abs(g0[s]).max())
+        if m < 1e-9:
+            continue
+        assert float(np.abs(g1[s] - g0[s]).max()) < 3e-2 * m, name
