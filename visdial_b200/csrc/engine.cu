@@ -528,7 +528,7 @@ void Engine::lstm_pair_forward(LstmRun& l1, LstmRun& l2, cudaStream_t sa, cudaSt
     cx.stream = sa;
     lstm_forward_begin(l1, true);               // h / c / gates of layer 1; gates1 <- x-projection + bias (batched GEMM)
     l2.x = l1.h;
-    l2.step_xproj = true;                       // no batched x-projection for layer 2: it is part of the fused K = 2H contraction
+    l2.step_xproj = true;                       // no batched x-projection for layer 2: the kernel's projection CTAs compute it per step
     lstm_forward_begin(l2, true);
     l1.h16 = arena.get<__half>((int64_t)T * R * H);
     l2.h16 = arena.get<__half>((int64_t)T * R * H);
