@@ -15,12 +15,18 @@ from helpers import small_batch, small_params, torch_batch, torch_params, flat_f
 from oracle import philox, visdial_oracle as O  # noqa: E402
 from visdial_b200 import init_parameters  # noqa: E402
 
-CASES = [("mn-att-ques-im-hist", "disc"), ("lf-ques", "gen"), ("hrea-ques-im-hist", "gen"), ("lf-ques-im-hist", "disc")]
+CASES = [("mn-att-ques-im-hist", "disc"), ("lf-ques", "gen"), ("hrea-ques-im-hist", "gen"), ("lf-ques-im-hist", "disc"),
+         # the seven sub-graph encoders, each with one decoder
+         ("lf-ques-im", "disc"), ("lf-ques-hist", "gen"), ("hre-ques-hist", "disc"), ("hre-ques-im-hist", "gen"),
+         ("mn-ques-hist", "gen"), ("mn-ques-im-hist", "disc"), ("lf-att-ques-im-hist", "disc")]
 
 
 def main():
     torch.set_num_threads(1)
     for enc, dec in CASES:
+        name = os.path.join(HERE, "%s__%s.npz" % (enc, dec))
+        if os.path.exists(name) and "--all" not in sys.argv:      # committed fixtures stay byte-identical; --all regenerates every one
+            continue
         p = small_params(enc, dec)
         flat = init_parameters(p, seed=21)
         nb = small_batch(p, B=2, seed=13, gen_eval=False)
@@ -38,7 +44,6 @@ def main():
             out["batch_" + k] = v
         if dec == "disc":
             out["ranks"] = O.compute_ranks(ev["decOut"]).numpy().astype(np.int32)
-        name = os.path.join(HERE, "%s__%s.npz" % (enc, dec))
         np.savez_compressed(name, **out)
         print(name, os.path.getsize(name), "bytes")
 
