@@ -414,10 +414,16 @@ struct EncBwdParams {
   const float* gates2; const float* c2; float* da2; __half* da2_16;
   const float* dh_last1; const float* dc_last1; const float* dh_last2; const float* dc_last2;   // (R,H) each or null
   const int32_t* mask;
-  int* flags;                      // [3][RB][T]
+  int* flags;                      // [3][RB][T] step flags, then (gate split) [2][RB][T][H/128] partial-sum counts
   unsigned long long* trace;       // null, or [grid][T][EP_TRACE_SLOTS]
+  float* dh2; float* dh1;          // gate split: (T*R, H) fp32 each, zeroed — the partial products of a step are summed here with red.add
 };
 
+// GS = gate split (H % 128 == 0): a CTA contracts ONE gate's quarter of the da panel (K = H) against a 128-unit slice of the weight
+// (same 128 KB): 32 tcgen05.mma of N = 128 per step instead of 128 of N = 32 — the step is bound by the instruction count
+// (profiles/r02_enc_trace.md) — and a quarter of the panel bytes.  The four gate CTAs of a unit slice add their partials into dh (red.add),
+// count themselves in, and each then runs the pointwise for 32 of the slice's 128 units once the count is complete.
+template <bool GS>
 __global__ void __launch_bounds__(EP_THREADS, 1)
 k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const EncBwdParams p) {
@@ -428,15 +434,21 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int per_group = 3 * p.nS;
   const int group = blockIdx.x / per_group, idx = blockIdx.x % per_group;
   const int role = idx / p.nS, slice = idx % p.nS;         // EP_CELL1 = T (layer 2), EP_PROJ = X, EP_CELL2 = B (layer 1)
-  constexpr int HS = EP_HS;                                // hidden units (= accumulator columns) of this slice
-  const int KB = 4 * H / 64;                               // k-blocks of one (rows, 4H) da panel = of the resident slice
+  constexpr int HS = EP_HS;                                // hidden units this CTA runs the pointwise for
+  constexpr int N = GS ? 128 : EP_HS;                      // accumulator columns
+  const int nU = H / 128;                                  // GS: unit slices of 128; slice = gate * nU + unit slice
+  const int gq = GS ? slice / nU : 0, us = GS ? slice % nU : 0;
+  const int j0 = GS ? us * 128 + gq * HS : slice * HS;     // first hidden unit of the pointwise
+  const int KB = (GS ? H : 4 * H) / 64;                    // k-blocks of the streamed panel (piece) = of the resident slice
   const int koff = ep_koff(role, slice, p.nS, KB);
   int* flagT = p.flags;
   int* flagX = p.flags + (size_t)p.RB * T;
   int* flagB = p.flags + 2 * (size_t)p.RB * T;
+  int* cntT = p.flags + 3 * (size_t)p.RB * T;              // GS: [RB][T][nU] partials summed into dh2 / dh1
+  int* cntB = cntT + (size_t)p.RB * T * nU;
 
   if (threadIdx.x == 0) sm.init_barriers();
-  if (warp == 1) tmem_alloc(sm.tmem_slot, 256);        // [0,32) accumulator, [32,256) seven staging slots (cell roles)
+  if (warp == 1) tmem_alloc(sm.tmem_slot, GS ? 512 : 256);   // [0,N) accumulator, then seven 32-column staging slots (cell roles)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -447,8 +459,9 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       // W2 = Wh2 as [H, 4H]; W1 = [Wx2 | Wh1] as [H, 8H]
       const CUtensorMap* tw = role == EP_CELL1 ? &tmW2 : &tmW1;
       const int kofs = role == EP_CELL2 ? 4 * H : 0;
-      mbar_expect_tx(sm.wbar, (uint32_t)(KB * HS * 128));
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sm.wsm + kb * HS * 128, tw, sm.wbar, kofs + kb * 64, slice * HS);
+      mbar_expect_tx(sm.wbar, (uint32_t)(KB * N * 128));
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d(sm.wsm + kb * N * 128, tw, sm.wbar, kofs + (GS ? gq * H : 0) + kb * 64, GS ? us * 128 : slice * HS);
       int s = 0; uint32_t ph = 0;
       for (int rb = group; rb < p.RB; rb += p.groups) {
         for (int t = T - 1; t >= 0; --t) {
@@ -465,7 +478,7 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             int kr = kb + koff; if (kr >= KB) kr -= KB;
             mbar_wait(&sm.empty[s], ph ^ 1);
             mbar_expect_tx(&sm.full[s], EP_STAGE_BYTES);
-            tma_load_2d(sm.stages + s * EP_STAGE_BYTES, tm, &sm.full[s], kr * 64, ts * p.R + rb * 128);
+            tma_load_2d(sm.stages + s * EP_STAGE_BYTES, tm, &sm.full[s], (GS ? gq * H : 0) + kr * 64, ts * p.R + rb * 128);
             if (++s == EP_STAGES) { s = 0; ph ^= 1; }
           }
           ep_stamp(p.trace, T, t, 1);
@@ -473,7 +486,7 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = ep_idesc_f16(128, HS);
+    const uint32_t idesc = ep_idesc_f16(128, N);
     mbar_wait(sm.wbar, 0);
     tc_fence_after();
     int s = 0; uint32_t ph = 0; uint32_t nuse = 0;
@@ -484,15 +497,45 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tc_fence_after();
         ++nuse;
         if (lane == 0) ep_stamp(p.trace, T, t, 2);
-        ep_mma_step(sm, tmem_base, idesc, KB, koff, HS, lane, s, ph, p.trace, T, t);
+        ep_mma_step(sm, tmem_base, idesc, KB, koff, N, lane, s, ph, p.trace, T, t);
       }
     }
   } else {
     const int q = warp & 3;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int j0 = slice * HS;
     uint32_t nuse = 0, nseen = 0;
-    if (role == EP_PROJ) {
+    // GS: add this CTA's (128 rows x 128 units) partial product into dh[t] and count it in for the unit slice
+    auto add_partial = [&](float* dhbuf, int* cnt, int rb, int t, int64_t tr, bool row_ok) {
+#pragma unroll
+      for (int sb = 0; sb < 4; ++sb) {
+        float a[32];
+        tmem_ld32(taddr + sb * 32, a); tmem_ld_wait();
+        if (row_ok) {
+          float* dst = dhbuf + tr * H + us * 128 + sb * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) red_add_v4(dst + e, a[e], a[e + 1], a[e + 2], a[e + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.tempty);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt + ((size_t)rb * T + t) * nU + us) : "memory");
+    };
+    if (role == EP_PROJ && GS) {
+      // partial of dh1_t = da2_t Wx2 (this gate's quarter, this unit slice), summed into dh1[t]
+      for (int rb = group; rb < p.RB; rb += p.groups) {
+        const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
+        const bool row_ok = row < p.R;
+        for (int t = T - 1; t >= 0; --t) {
+          mbar_wait(sm.tfull, nuse & 1); tc_fence_after(); ++nuse;
+          if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 4);
+          if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 5);
+          add_partial(p.dh1, cntB, rb, t, (int64_t)t * p.R + row, row_ok);
+          if (threadIdx.x == 64) { ep_stamp(p.trace, T, t, 6); ep_stamp(p.trace, T, t, 7, true); }
+        }
+      }
+    } else if (role == EP_PROJ) {
       // partial of dh1_t = da2_t Wx2, parked in the first H columns of da1[t] (the B cell of the same slice reads it, then overwrites)
       for (int rb = group; rb < p.RB; rb += p.groups) {
         const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
@@ -526,7 +569,9 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const float* dh_last = top ? p.dh_last2 : p.dh_last1;
       const float* dc_last = top ? p.dc_last2 : p.dc_last1;
       int* flag = top ? flagT : flagB;
-      const uint32_t tstage = taddr + 32;
+      const uint32_t tstage = taddr + N;
+      float* dhbuf = top ? p.dh2 : p.dh1;
+      int* cnt = top ? cntT : cntB;
       for (int rb = group; rb < p.RB; rb += p.groups) {
         const int64_t row = (int64_t)rb * 128 + q * 32 + lane;
         const bool row_ok = row < p.R;
@@ -543,13 +588,13 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           // everything the pointwise reads besides the contraction (saved gates, c_t, c_{t-1}, the parked partial) goes to the TMEM staging
           // columns while the contraction of this step is still running; da_t overwrites the gate columns in place
           // staging map: S0 = o -> da_o, S1 = c_t, S2 = i -> da_i, S3 = g -> da_g, S4 = f -> da_f, S5 = c_{t-1}, S6 = partial
-          if (!top) wait_flag_generic(flagX + (size_t)rb * T + t, p.nS);     // the parked partial of this step is in place
+          if (!GS && !top) wait_flag_generic(flagX + (size_t)rb * T + t, p.nS);     // the parked partial of this step is in place
           {
             const float* src[7] = {grow + 2 * H, cst + tr * H + j0, grow, grow + 3 * H, grow + 1 * H,
-                                   t > 0 ? cst + (tr - p.R) * H + j0 : nullptr, top ? nullptr : darow};
+                                   t > 0 ? cst + (tr - p.R) * H + j0 : nullptr, (top || GS) ? nullptr : darow};
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
-              if (k == 6 && top) continue;
+              if (k == 6 && (top || GS)) continue;
               if (row_ok && src[k]) ld32g(src[k], va); else zero32(va);
               tmem_st32(tstage + k * HS, va);
             }
@@ -557,16 +602,29 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           tmem_st_wait();
           if (has_acc) { mbar_wait(sm.tfull, nuse & 1); tc_fence_after(); ++nuse; }
           if (threadIdx.x == 64) ep_stamp(p.trace, T, t, 4);
-          if (has_acc) tmem_ld32(taddr, dh); else zero32(dh);
-          tmem_ld32(tstage + 0 * HS, va); tmem_ld32(tstage + 1 * HS, vb); tmem_ld_wait();
-          if (has_acc) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sm.tempty);
-          }
-          if (!top) { float pp[HS]; tmem_ld32(tstage + 6 * HS, pp); tmem_ld_wait();
+          if constexpr (GS) {
+            // my partial into dh[t]; then the complete sum of my 32 units once every contributor of the unit slice has counted in:
+            // layer 2: its 4 gate CTAs; layer 1: 4 projection CTAs (every step) + its own 4 gate CTAs (all steps but the last)
+            if (has_acc) add_partial(dhbuf, cnt, rb, t, tr, row_ok);
+            const int want = top ? 4 : (has_acc ? 8 : 4);
+            if (top && !has_acc) zero32(dh);
+            else {
+              wait_flag_generic(cnt + ((size_t)rb * T + t) * nU + us, want);
+              if (row_ok) ld32g(dhbuf + tr * H + j0, dh); else zero32(dh);
+            }
+            tmem_ld32(tstage + 0 * HS, va); tmem_ld32(tstage + 1 * HS, vb); tmem_ld_wait();
+          } else {
+            if (has_acc) tmem_ld32(taddr, dh); else zero32(dh);
+            tmem_ld32(tstage + 0 * HS, va); tmem_ld32(tstage + 1 * HS, vb); tmem_ld_wait();
+            if (has_acc) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(sm.tempty);
+            }
+            if (!top) { float pp[HS]; tmem_ld32(tstage + 6 * HS, pp); tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < HS; ++e) dh[e] += pp[e]; }
+              for (int e = 0; e < HS; ++e) dh[e] += pp[e]; }
+          }
           if (t == T - 1 && row_ok) {
             if (dh_last) { float pp[HS]; ld32g(dh_last + row * H + j0, pp);
 #pragma unroll
@@ -615,7 +673,7 @@ k_enc_pair_bwd(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, GS ? 512 : 256); }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -730,13 +788,20 @@ void enc_pair_forward(LaunchCtx& cx, int T, int64_t R, int H, const __half* W1h1
 }
 
 
-// gates*/c* = the activations the forward saved; da*/da*_16 out (all T steps); flags int32 [3 * RB * T]
+// gates*/c* = the activations the forward saved; da*/da*_16 out (all T steps); flags int32 [enc_pair_bwd_flag_ints()].
+// dh1 / dh2: (T*R, H) fp32 scratch each for the gate-split variant (H % 128 == 0), or null -> unit-split variant
+int64_t enc_pair_bwd_flag_ints(int T, int64_t R, int H) { return (int64_t)cdiv(R, 128) * T * (3 + 2 * std::max(1, H / 128)); }
+bool enc_pair_gate_split(int H) {
+  static const int v = [] { const char* e = getenv("VD_ENC_GATESPLIT"); return e ? atoi(e) : 1; }();      // VD_ENC_GATESPLIT=0: unit split
+  return v != 0 && H % 128 == 0;
+}
 void enc_pair_backward(LaunchCtx& cx, int T, int64_t R, int H, const __half* B1cat16, const __half* Whb2_16, const int32_t* mask,
                        const float* gates1, const float* c1, const float* gates2, const float* c2, const float* dh_last1,
                        const float* dc_last1, const float* dh_last2, const float* dc_last2, float* da1, __half* da1_16, float* da2,
-                       __half* da2_16, int* flags) {
+                       __half* da2_16, int* flags, float* dh1, float* dh2) {
   using namespace tc;
   VD_REQUIRE(enc_pair_shape_ok(R, H, cx.sm_count), VD_E_STATE, "enc_pair_backward: shape");
+  const bool gs = dh1 && dh2 && enc_pair_gate_split(H);
   EncBwdParams p = {};
   p.T = T; p.R = (int)R; p.H = H; p.RB = cdiv(R, 128);
   p.nS = H / 32;
@@ -744,22 +809,29 @@ void enc_pair_backward(LaunchCtx& cx, int T, int64_t R, int H, const __half* B1c
   p.gates1 = gates1; p.c1 = c1; p.da1 = da1; p.da1_16 = da1_16;
   p.gates2 = gates2; p.c2 = c2; p.da2 = da2; p.da2_16 = da2_16;
   p.dh_last1 = dh_last1; p.dc_last1 = dc_last1; p.dh_last2 = dh_last2; p.dc_last2 = dc_last2;
-  p.mask = mask; p.flags = flags;
-  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)3 * p.RB * T * sizeof(int), cx.stream));
+  p.mask = mask; p.flags = flags; p.dh1 = dh1; p.dh2 = dh2;
+  VD_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)enc_pair_bwd_flag_ints(T, R, H) * sizeof(int), cx.stream));
   const int64_t TR = (int64_t)T * R;
   const int64_t G = 4 * (int64_t)H;
+  if (gs) {
+    VD_CUDA_CHECK(cudaMemsetAsync(dh1, 0, (size_t)TR * H * sizeof(float), cx.stream));
+    VD_CUDA_CHECK(cudaMemsetAsync(dh2, 0, (size_t)TR * H * sizeof(float), cx.stream));
+  }
   CUtensorMap tA1 = ep_tmap_h(da1_16, TR, G, G, 128), tA2 = ep_tmap_h(da2_16, TR, G, G, 128);
-  CUtensorMap tW1 = ep_tmap_h(B1cat16, H, 2 * G, 2 * G, EP_HS), tW2 = ep_tmap_h(Whb2_16, H, G, G, EP_HS);
+  const int wbox = gs ? 128 : EP_HS;
+  CUtensorMap tW1 = ep_tmap_h(B1cat16, H, 2 * G, 2 * G, wbox), tW2 = ep_tmap_h(Whb2_16, H, G, G, wbox);
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA_CHECK(cudaFuncSetAttribute(k_enc_pair_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM));
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_enc_pair_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM));
+    VD_CUDA_CHECK(cudaFuncSetAttribute(k_enc_pair_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EP_SMEM));
     attr_set = true;
   }
   EpTrace trace;
   p.trace = trace.begin(p.groups * 3 * p.nS, T);
-  k_enc_pair_bwd<<<p.groups * 3 * p.nS, EP_THREADS, EP_SMEM, cx.stream>>>(tA1, tA2, tW1, tW2, p);
+  if (gs) k_enc_pair_bwd<true><<<p.groups * 3 * p.nS, EP_THREADS, EP_SMEM, cx.stream>>>(tA1, tA2, tW1, tW2, p);
+  else k_enc_pair_bwd<false><<<p.groups * 3 * p.nS, EP_THREADS, EP_SMEM, cx.stream>>>(tA1, tA2, tW1, tW2, p);
   check_launch(cx, "k_enc_pair_bwd");
-  trace.report(cx.stream, "bwd", p.nS, true);
+  trace.report(cx.stream, gs ? "bwd(gate split)" : "bwd", p.nS, true);
 }
 
 }  // namespace vd

@@ -737,11 +737,13 @@ void Engine::lstm_pair_backward(LstmRun& l1, LstmRun& l2, const float* dh_last2,
     cvt_f32_to_f16(cx, Whb2, G, Wp(l2.wseg) + (int64_t)l2.D * G, G, H, G);                 // Wh2: rows D2.. of (D2+H, 4H)
     cvt_f32_to_f16(cx, B1cat, 2 * G, Wp(l2.wseg), G, H, G);                                 // [Wx2 | ...]: rows 0..H-1 of layer 2
     cvt_f32_to_f16(cx, B1cat + G, 2 * G, Wp(l1.wseg) + (int64_t)l1.D * G, G, H, G);         // [... | Wh1]
-    int* flags = arena.get<int>(3 * (int64_t)cdiv(R, 128) * T);
+    int* flags = arena.get<int>(enc_pair_bwd_flag_ints(T, R, H));
+    float* dh1 = nullptr; float* dh2 = nullptr;
+    if (enc_pair_gate_split(H)) { dh1 = arena.get<float>(TR * H); dh2 = arena.get<float>(TR * H); }
     {
       LaunchCtx::Scope sc2(&cx, "enc_pair_bwd", 2.0 * T * R * (double)H * 3.0 * G, 4.0 * T * R * (4.0 * G + 4.0 * H));
       enc_pair_backward(cx, T, R, H, B1cat, Whb2, l1.mask, l1.gates, l1.c, l2.gates, l2.c, dh_last1, dc_last1, dh_last2, dc_last2,
-                        l1.da, l1.da16, l2.da, l2.da16, flags);
+                        l1.da, l1.da16, l2.da, l2.da16, flags, dh1, dh2);
     }
     lstm_backward_end(l2, nullptr, nullptr, nullptr);
     lstm_backward_end(l1, dx1_out, nullptr, nullptr);
