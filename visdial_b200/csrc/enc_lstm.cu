@@ -14,6 +14,9 @@
 //   BPTT      T   cell of layer 2:   dh2_t = da2_{t+1} Wh2 [+ dL/dh2 at the last step]                -> da2_t     K = 4H
 //             X   input half:        da1[t][:, 0:H] <- da2_t Wx2    (partial of dh1_t, parked in the output rows)  K = 4H
 //             B   cell of layer 1:   dh1_t = partial + da1_{t+1} Wh1 [+ dL/dh1 at the last step]      -> da1_t     K = 4H
+//   (BPTT as listed = k_enc_pair_bwd<false>, the split by hidden unit.  The default when H % 128 == 0 is the split BY GATE,
+//   k_enc_pair_bwd<true>: CTA (gate, 128-unit slice) contracts K = H against N = 128 and the four gate CTAs of a slice sum their
+//   partials in a zeroed fp32 dh[t] with red.add before each runs the pointwise of 32 units — see the comment at the kernel.)
 //
 // (Measured with the phase trace below, round 2: with the layer-2 cell contracting [h1_t | h2_{t-1}] itself, and the layer-1
 // BPTT cell [da2_t | da1_{t+1}], the two-panel role set the step time: 21.9k clk forward, 45.6k clk BPTT, of which the
